@@ -1,0 +1,205 @@
+"""ctypes binding of libdiffmpc_b200.so (C ABI: include/diffmpc_b200.h).
+
+This is the only bridge between the Python facade modules (lqr/, mpc/) and the
+sm_100a kernels.  There is NO CPU fallback: importing works without a GPU (so
+the symbol table can be checked), but creating a context raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdiffmpc_b200.so")
+
+F64, F32 = 0, 1
+LQR_FACTOR, LQR_ROLLOUT, LQR_SAVE_FAC = 1, 2, 4
+ADJ_STRICT_REFERENCE = 1
+COUPLING_ELEMENT, COUPLING_BATCH = 0, 1
+DYN_LINEAR, DYN_PENDULUM = 0, 1
+FLAG_QP_NOT_CONVERGED, FLAG_NONFINITE, FLAG_LS_CAPPED = 1, 2, 4
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_sz = ctypes.c_size_t
+_d = ctypes.c_double
+
+# name -> (restype, argtypes); must list every symbol declared in include/diffmpc_b200.h
+SIGNATURES = {
+    "dmpc_version": (_i, []),
+    "dmpc_status_string": (ctypes.c_char_p, [_i]),
+    "dmpc_create": (_i, [_i, ctypes.POINTER(_vp)]),
+    "dmpc_destroy": (_i, [_vp]),
+    "dmpc_last_error": (ctypes.c_char_p, [_vp]),
+    "dmpc_device_count": (_i, []),
+    "dmpc_malloc": (_i, [_vp, _sz, ctypes.POINTER(_vp)]),
+    "dmpc_free": (_i, [_vp, _vp]),
+    "dmpc_host_alloc": (_i, [_vp, _sz, ctypes.POINTER(_vp)]),
+    "dmpc_host_free": (_i, [_vp, _vp]),
+    "dmpc_memcpy_h2d": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "dmpc_memcpy_d2h": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "dmpc_memset": (_i, [_vp, _vp, _i, _sz, _vp]),
+    "dmpc_sync": (_i, [_vp, _vp]),
+    "dmpc_launch_count": (ctypes.c_longlong, [_vp]),
+    "dmpc_lqr_fac_elems": (_sz, [_i, _i, _i, _i]),
+    "dmpc_lqr_solve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "dmpc_lqr_adjoint": (_i, [_vp, _i, _i, _i, _i, _i] + [_vp] * 14 + [_i, _vp]),
+}
+
+_lib = None
+
+
+class DiffMpcError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the in-tree shared library and type every entry point.  Raises if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DiffMpcError(
+            "libdiffmpc_b200.so not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C chainer-differentiable-mpc_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def dtype_code(dt):
+    dt = np.dtype(dt)
+    if dt == np.float64:
+        return F64
+    if dt == np.float32:
+        return F32
+    raise DiffMpcError("unsupported dtype %s (float64 / float32 only)" % dt)
+
+
+class DeviceArray:
+    """A typed, shaped cudaMalloc'ed buffer owned by a Context."""
+
+    def __init__(self, ctx, shape, dtype):
+        self.ctx = ctx
+        self.shape = tuple(int(v) for v in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = _vp()
+        ctx._check(ctx.lib.dmpc_malloc(ctx.h, self.nbytes, ctypes.byref(p)))
+        self.ptr = p.value
+        self._owned = True
+
+    def upload(self, arr, stream=None):
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
+        assert arr.shape == self.shape, (arr.shape, self.shape)
+        self.ctx._check(self.ctx.lib.dmpc_memcpy_h2d(self.ctx.h, self.ptr, arr.ctypes.data, self.nbytes, stream))
+        # pageable memcpyAsync returns after staging, so `arr` may be released
+        return self
+
+    def download(self, out=None, stream=None):
+        if out is None:
+            out = np.empty(self.shape, dtype=self.dtype)
+        assert out.flags["C_CONTIGUOUS"] and out.nbytes == self.nbytes
+        self.ctx._check(self.ctx.lib.dmpc_memcpy_d2h(self.ctx.h, out.ctypes.data, self.ptr, self.nbytes, stream))
+        self.ctx.sync(stream)
+        return out
+
+    def zero(self, stream=None):
+        self.ctx._check(self.ctx.lib.dmpc_memset(self.ctx.h, self.ptr, 0, self.nbytes, stream))
+        return self
+
+    def free(self):
+        if self._owned and self.ptr and self.ctx.h:
+            self.ctx.lib.dmpc_free(self.ctx.h, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _p(x):
+    if x is None:
+        return None
+    if isinstance(x, DeviceArray):
+        return x.ptr
+    return int(x)       # raw device pointer (e.g. torch.Tensor.data_ptr())
+
+
+class Context:
+    """One handle per device (cudaStream + launch counter)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = None
+        h = _vp()
+        rc = self.lib.dmpc_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise DiffMpcError("dmpc_create(device=%d) failed: %s" % (device, self.lib.dmpc_status_string(rc).decode()))
+        self.h = h
+        self.device = int(device)
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.dmpc_status_string(rc).decode()
+            det = self.lib.dmpc_last_error(self.h).decode() if self.h else ""
+            if rc in (1, 2, 3):
+                raise AssertionError("%s: %s" % (msg, det))     # the reference raises AssertionError here
+            raise DiffMpcError("%s: %s" % (msg, det))
+
+    def close(self):
+        if self.h:
+            self.lib.dmpc_destroy(self.h)
+            self.h = None
+
+    def sync(self, stream=None):
+        self._check(self.lib.dmpc_sync(self.h, stream))
+
+    @property
+    def launches(self):
+        return int(self.lib.dmpc_launch_count(self.h))
+
+    def empty(self, shape, dtype=np.float64):
+        return DeviceArray(self, shape, dtype)
+
+    def zeros(self, shape, dtype=np.float64):
+        return DeviceArray(self, shape, dtype).zero()
+
+    def to_device(self, arr, dtype=None):
+        arr = np.asarray(arr)
+        if dtype is None:
+            dtype = arr.dtype
+        return DeviceArray(self, arr.shape, dtype).upload(arr)
+
+    # ---- kernels ---------------------------------------------------------------------
+    def lqr_solve(self, dtype, T, B, n, m, x0, C, c, F, F_T, f, x, u, Ks, ks, fac=None,
+                  flags=LQR_FACTOR | LQR_ROLLOUT, stream=None):
+        self._check(self.lib.dmpc_lqr_solve(self.h, dtype_code(dtype), T, B, n, m, _p(x0), _p(C), _p(c), _p(F), F_T,
+                                            _p(f), _p(x), _p(u), _p(Ks), _p(ks), _p(fac), flags, stream))
+
+    def lqr_adjoint(self, dtype, T, B, n, m, C, c, F, x, u, gx, gu, Ks, fac, dx0, dC, dc, dF, df,
+                    flags=ADJ_STRICT_REFERENCE, stream=None):
+        self._check(self.lib.dmpc_lqr_adjoint(self.h, dtype_code(dtype), T, B, n, m, _p(C), _p(c), _p(F), _p(x), _p(u),
+                                              _p(gx), _p(gu), _p(Ks), _p(fac), _p(dx0), _p(dC), _p(dc), _p(dF),
+                                              _p(df), flags, stream))
+
+    def lqr_fac_elems(self, T, B, n, m):
+        return int(self.lib.dmpc_lqr_fac_elems(T, B, n, m))
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    """Process-wide context per device (created on first use; raises without a GPU)."""
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        _default_ctx[device] = ctx
+    return ctx

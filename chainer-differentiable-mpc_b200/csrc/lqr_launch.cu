@@ -1,0 +1,94 @@
+// Kernel instantiation + shape dispatch for the LQR kernels (lqr_kernels.cuh).
+#include "launch.h"
+
+namespace dmpc {
+
+// Compile-time shapes: the BASELINE.json configs + the reference's examples.
+//   (3,1) pendulum / Boyd / LQRnet   (2,1) one-variable example   (4,2) c2   (8,4) c3   (32,8) c5
+#define DMPC_SHAPES(X) X(2, 1, 4) X(3, 1, 4) X(4, 2, 8) X(8, 4, 16) X(32, 8, 256)
+
+ShapeInfo pick_shape(int n, int m) {
+#define X(N_, M_, G_) if (n == N_ && m == M_) return ShapeInfo{N_, M_, G_, true};
+  DMPC_SHAPES(X)
+#undef X
+  const int s = n + m;
+  int G = s <= 6 ? 8 : (s <= 14 ? 16 : (s <= 24 ? 32 : 256));
+  return ShapeInfo{n, m, G, false};
+}
+
+template <int G> struct Tpb { static constexpr int value = (G <= 32) ? 128 : G; };
+
+template <typename K, typename P>
+static int do_launch(K kernel, const P& p, int G, size_t stride_bytes, int B, cudaStream_t st, long long* nl) {
+  int tpb = (G <= 32) ? 128 : G;
+  int epb = (G <= 32) ? tpb / G : 1;
+  while (G <= 32 && (size_t)epb * stride_bytes > (size_t)kMaxSmem && tpb > 32) { tpb /= 2; epb = tpb / G; }
+  // small batches: fewer elements per CTA so the grid covers more SMs
+  while (G <= 32 && tpb > 32 && (B + epb - 1) / epb < 148 * 2) { tpb /= 2; epb = tpb / G; }
+  const size_t smem = (size_t)epb * stride_bytes;
+  if (smem > (size_t)kMaxSmem) return DMPC_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return DMPC_ERR_CUDA;
+  const int grid = (B + epb - 1) / epb;
+  kernel<<<grid, tpb, smem, st>>>(p);
+  if (nl) ++*nl;
+  return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+}
+
+template <typename R>
+int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
+  const ShapeInfo si = pick_shape(p.n, p.m);
+  const LqrLayout L = lqr_layout<R>(p.n, p.m, (p.flags & LQR_SAVE_FAC) != 0);
+  const size_t sb = (size_t)L.stride * sizeof(R);
+#define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) return do_launch(lqr_solve_kernel<R, N_, M_, G_>, p, G_, sb, p.B, st, nl);
+  DMPC_SHAPES(X)
+#undef X
+  if (p.m > 32) return DMPC_ERR_UNSUPPORTED;
+  switch (si.G) {
+    case 8: return do_launch(lqr_solve_kernel<R, 0, 0, 8>, p, 8, sb, p.B, st, nl);
+    case 16: return do_launch(lqr_solve_kernel<R, 0, 0, 16>, p, 16, sb, p.B, st, nl);
+    case 32: return do_launch(lqr_solve_kernel<R, 0, 0, 32>, p, 32, sb, p.B, st, nl);
+    default: return do_launch(lqr_solve_kernel<R, 0, 0, 256>, p, 256, sb, p.B, st, nl);
+  }
+}
+
+template <typename R>
+int launch_lqr_dtau(const DtauParams<R>& p, cudaStream_t st, long long* nl) {
+  const ShapeInfo si = pick_shape(p.n, p.m);
+  const DtauLayout L = dtau_layout<R>(p.n, p.m);
+  const size_t sb = (size_t)L.stride * sizeof(R);
+#define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) return do_launch(lqr_dtau_kernel<R, N_, M_, (G_ > 32 ? 64 : G_)>, p, (G_ > 32 ? 64 : G_), sb, p.B, st, nl);
+  DMPC_SHAPES(X)
+#undef X
+  switch (si.G) {
+    case 8: return do_launch(lqr_dtau_kernel<R, 0, 0, 8>, p, 8, sb, p.B, st, nl);
+    case 16: return do_launch(lqr_dtau_kernel<R, 0, 0, 16>, p, 16, sb, p.B, st, nl);
+    case 32: return do_launch(lqr_dtau_kernel<R, 0, 0, 32>, p, 32, sb, p.B, st, nl);
+    default: return do_launch(lqr_dtau_kernel<R, 0, 0, 64>, p, 64, sb, p.B, st, nl);
+  }
+}
+
+template <typename R>
+int launch_adjoint_out(const AdjOutParams<R>& p, cudaStream_t st, long long* nl) {
+  const ShapeInfo si = pick_shape(p.n, p.m);
+  const AdjLayout L = adj_layout<R>(p.n, p.m);
+  const size_t sb = (size_t)L.stride * sizeof(R);
+#define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) return do_launch(adjoint_out_kernel<R, N_, M_, (G_ > 32 ? 128 : G_)>, p, (G_ > 32 ? 128 : G_), sb, p.B, st, nl);
+  DMPC_SHAPES(X)
+#undef X
+  switch (si.G) {
+    case 8: return do_launch(adjoint_out_kernel<R, 0, 0, 8>, p, 8, sb, p.B, st, nl);
+    case 16: return do_launch(adjoint_out_kernel<R, 0, 0, 16>, p, 16, sb, p.B, st, nl);
+    case 32: return do_launch(adjoint_out_kernel<R, 0, 0, 32>, p, 32, sb, p.B, st, nl);
+    default: return do_launch(adjoint_out_kernel<R, 0, 0, 128>, p, 128, sb, p.B, st, nl);
+  }
+}
+
+template int launch_lqr_solve<double>(const LqrParams<double>&, cudaStream_t, long long*);
+template int launch_lqr_solve<float>(const LqrParams<float>&, cudaStream_t, long long*);
+template int launch_lqr_dtau<double>(const DtauParams<double>&, cudaStream_t, long long*);
+template int launch_lqr_dtau<float>(const DtauParams<float>&, cudaStream_t, long long*);
+template int launch_adjoint_out<double>(const AdjOutParams<double>&, cudaStream_t, long long*);
+template int launch_adjoint_out<float>(const AdjOutParams<float>&, cudaStream_t, long long*);
+
+}  // namespace dmpc

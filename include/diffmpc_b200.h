@@ -1,0 +1,129 @@
+/*
+ * diffmpc_b200 - C ABI of the B200-native batched LQR / box-DDP solver.
+ *
+ * Drop-in boundary for the hot path of pfnet-research/chainer-differentiable-mpc.
+ * Every entry point states the reference interface it replaces (file:line in the
+ * reference tree).  The reference is pure Python/NumPy, so "the FFI a maintainer
+ * would bind" is ctypes: see INTEGRATION.md for the stubs.
+ *
+ * Conventions
+ *   - All tensors use the reference's layout: time-major, batch-second, C-contiguous
+ *     (lqr_recursion.py:51-66):  x_init[B,n] C[T,B,s,s] c[T,B,s] F[F_T,B,n,s] f[T-1,B,n]
+ *     x[T,B,n] u[T,B,m]   with s = n + m and F_T in {T-1, T} (mpc_step.py:83-89).
+ *   - dtype: DMPC_F64 (the reference is float64 end to end) or DMPC_F32.
+ *   - Pointers named d_* are DEVICE pointers; the call is asynchronous on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the handle's stream).
+ *   - Pointers named h_* are HOST pointers; those entry points copy in/out and
+ *     synchronise before returning (they are what the Python facade uses).
+ *   - Return value: 0 on success, else a dmpc_status; dmpc_last_error() has detail.
+ *   - The library never falls back to a CPU path: without a CUDA device
+ *     dmpc_create() returns DMPC_ERR_NO_DEVICE.
+ *   - Inputs are never modified (pnqp.py:86, util.py:496,514 make copies);
+ *     the caller owns every buffer.
+ */
+#ifndef DIFFMPC_B200_H
+#define DIFFMPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dmpc_ctx* dmpc_handle;
+
+enum dmpc_dtype { DMPC_F64 = 0, DMPC_F32 = 1 };
+
+enum dmpc_status {
+  DMPC_OK = 0,
+  DMPC_ERR_BAD_SHAPE = 1,   /* the reference's shape asserts (lqr_recursion.py:51-66, mpc_step.py:79-92) */
+  DMPC_ERR_BAD_BOUNDS = 2,  /* lower > upper (pnqp.py:64, mpc_step.py:139) */
+  DMPC_ERR_NONFINITE = 3,   /* NaN / inf asserts (mpc_step.py:133-135,161-162,284-285) */
+  DMPC_ERR_CUDA = 4,
+  DMPC_ERR_UNSUPPORTED = 5,
+  DMPC_ERR_NULL = 6,
+  DMPC_ERR_NO_DEVICE = 7
+};
+
+/* per-element flag bits reported in `d_flags[B]` (int32) */
+enum dmpc_elem_flag {
+  DMPC_FLAG_QP_NOT_CONVERGED = 1, /* pnqp.py:192 "Did not converge" warning */
+  DMPC_FLAG_NONFINITE = 2,
+  DMPC_FLAG_LS_CAPPED = 4         /* line search hit the safety cap (mpc_step.py:196 would not terminate) */
+};
+
+/* lqr_solve flags */
+enum {
+  DMPC_LQR_FACTOR = 1,   /* LqrRecursion.backward (lqr_recursion.py:69-158): Riccati sweep -> Ks, ks */
+  DMPC_LQR_ROLLOUT = 2,  /* LqrRecursion.forward  (lqr_recursion.py:160-200): x, u from Ks, ks */
+  DMPC_LQR_SAVE_FAC = 4  /* also store Quu^-1 and Qxu per (t,b) for dmpc_lqr_adjoint */
+};
+
+/* adjoint flags */
+enum {
+  DMPC_ADJ_STRICT_REFERENCE = 1 /* reproduce differentiable_lqr.py:128 (dC precedence) and :133 (df shift) */
+};
+
+/* coupling of the batch-global control flow of PNQP */
+enum dmpc_coupling { DMPC_COUPLING_ELEMENT = 0, DMPC_COUPLING_BATCH = 1 };
+
+/* true-dynamics selector for the line-search rollout (mpc_step.py:229-240) */
+enum dmpc_dynamics { DMPC_DYN_LINEAR = 0, DMPC_DYN_PENDULUM = 1 };
+
+/* ---- library / context ------------------------------------------------------------- */
+int dmpc_version(void);
+const char* dmpc_status_string(int status);
+int dmpc_create(int device, dmpc_handle* out);
+int dmpc_destroy(dmpc_handle h);
+const char* dmpc_last_error(dmpc_handle h);
+int dmpc_device_count(void);
+
+/* ---- memory / stream helpers (so a ctypes host needs no other CUDA binding) ---------- */
+int dmpc_malloc(dmpc_handle h, size_t bytes, void** d_ptr);
+int dmpc_free(dmpc_handle h, void* d_ptr);
+int dmpc_host_alloc(dmpc_handle h, size_t bytes, void** h_ptr); /* pinned */
+int dmpc_host_free(dmpc_handle h, void* h_ptr);
+int dmpc_memcpy_h2d(dmpc_handle h, void* d_dst, const void* h_src, size_t bytes, void* stream);
+int dmpc_memcpy_d2h(dmpc_handle h, void* h_dst, const void* d_src, size_t bytes, void* stream);
+int dmpc_memset(dmpc_handle h, void* d_dst, int value, size_t bytes, void* stream);
+int dmpc_sync(dmpc_handle h, void* stream);
+/* number of kernels this handle has launched (bench.py's gpu_launches) */
+long long dmpc_launch_count(dmpc_handle h);
+
+/* ---- LQR (replaces LqrRecursion, lqr/lqr_recursion.py:18-209) ------------------------ */
+/* elements (not bytes) of the factor cache written with DMPC_LQR_SAVE_FAC */
+size_t dmpc_lqr_fac_elems(int T, int B, int n, int m);
+
+/*
+ * LqrRecursion.solve_recursion / .backward / .forward (lqr_recursion.py:202, :69, :160).
+ *   flags = FACTOR|ROLLOUT  -> solve_recursion: writes d_Ks, d_ks, d_x, d_u
+ *   flags = FACTOR          -> backward(): writes d_Ks[T,B,m,n], d_ks[T,B,m]
+ *   flags = ROLLOUT         -> forward(Ks, ks): reads d_Ks, d_ks, writes d_x, d_u
+ * d_f may be NULL (f is None).  d_fac may be NULL unless SAVE_FAC.
+ */
+int dmpc_lqr_solve(dmpc_handle h, int dtype, int T, int B, int n, int m,
+                   const void* d_x0, const void* d_C, const void* d_c,
+                   const void* d_F, int F_T, const void* d_f,
+                   void* d_x, void* d_u, void* d_Ks, void* d_ks, void* d_fac,
+                   int flags, void* stream);
+
+/*
+ * DiffLqr.backward (lqr/differentiable_lqr.py:78-142).  Needs d_Ks and d_fac from a
+ * dmpc_lqr_solve(... FACTOR|SAVE_FAC) on the same C, F.  Outputs have the shapes of
+ * the inputs: d_dx0[B,n] d_dC[T,B,s,s] d_dc[T,B,s] d_dF[T-1,B,n,s] d_df[T-1,B,n] (nullable).
+ * With DMPC_ADJ_STRICT_REFERENCE the reference's dC / df quirks (Q1, Q2) are reproduced;
+ * without it the mathematically correct gradients are returned.
+ */
+int dmpc_lqr_adjoint(dmpc_handle h, int dtype, int T, int B, int n, int m,
+                     const void* d_C, const void* d_c, const void* d_F,
+                     const void* d_x, const void* d_u,
+                     const void* d_gx, const void* d_gu,
+                     const void* d_Ks, const void* d_fac,
+                     void* d_dx0, void* d_dC, void* d_dc, void* d_dF, void* d_df,
+                     int flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFMPC_B200_H */
