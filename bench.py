@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py - LQR fwd+bwd solves/s (DiffLqr.apply + .backward) on B200, one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c5|c2|c3s] [--impl reference]
+
+Metric (BASELINE.json): "LQR fwd+bwd solves/sec"; one solve = one batch element's full
+horizon through forward (Riccati + rollout) and the KKT-adjoint backward.
+Default workload = BASELINE config 5 shape (n=32, m=8, T=100, fp64), weak-scaled:
+8192 elements per GPU, i.e. batch 65536 on 8 GPUs (the full batch is 154 GB of inputs
+and does not fit one GPU).  The batch dimension is sharded with no inter-GPU traffic
+inside a solve -> "scaling": "weak".
+
+The oracle (oracle/) is imported only for the cpu_baseline leg / --impl reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "chainer-differentiable-mpc_b200")
+for p in (ROOT, PKG, os.path.join(PKG, "lqr"), os.path.join(PKG, "mpc")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (n, m, T, B per GPU, description)
+    "c5": (32, 8, 100, 8192, "BASELINE config 5: LQR n=32 m=8 T=100 fp64, 8192 elements/GPU (65536 on 8 GPUs)"),
+    "c2": (4, 2, 50, 4096, "BASELINE config 2: LQR n=4 m=2 T=50 B=4096 fp64"),
+    "c3s": (8, 4, 50, 16384, "BASELINE config 3 shape, unconstrained LQR fwd+bwd n=8 m=4 T=50 B=16384 fp64"),
+    "c4s": (3, 1, 20, 8192, "pendulum shape LQR fwd+bwd n=3 m=1 T=20 B=8192/GPU fp64"),
+}
+
+
+def algorithmic_bytes(n, m, T, w=8):
+    """compulsory traffic of fwd+bwd at the operator boundary, per solve."""
+    s = n + m
+    fwd = w * (n + T * s * s + T * s + (T - 1) * n * s + (T - 1) * n) + w * T * s
+    bwd = w * (T * s * s + T * s + (T - 1) * n * s + 2 * T * s) + w * (n + T * s * s + T * s + (T - 1) * n * s + (T - 1) * n)
+    return fwd, fwd + bwd
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._th = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------- CPU port timing
+def cpu_lqr_fwd_bwd(n, m, T, Bc, seed=0):
+    """One DiffLqr.apply + .backward with the oracle port (numpy, all BLAS threads)."""
+    from oracle import lqr as olqr
+    from tests_helpers_local import lqr_problem_np
+    pr = lqr_problem_np(seed, T, Bc, n, m)
+    rs = np.random.RandomState(1)
+    gx, gu = rs.randn(T, Bc, n), rs.randn(T, Bc, m)
+    t0 = time.perf_counter()
+    x, u, _, _ = olqr.lqr_solve(pr["x0"], pr["C"], pr["c"], pr["F"], pr["f"], n, m)
+    olqr.difflqr_backward(pr["x0"], pr["C"], pr["c"], pr["F"], x, u, gx, gu, n, m)
+    return time.perf_counter() - t0
+
+
+def cpu_sample_batch(n, m, T):
+    # sized so one fwd+bwd takes a few seconds on ~8 host cores
+    return {(32, 8): 128, (8, 4): 1024, (4, 2): 4096, (3, 1): 4096}.get((n, m), 256)
+
+
+def run_reference(args):
+    n, m, T, Bg, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Bc = cpu_sample_batch(n, m, T)
+    for _ in range(max(args.warmup, 1)):
+        cpu_lqr_fwd_bwd(n, m, T, Bc)
+    times = [cpu_lqr_fwd_bwd(n, m, T, Bc) for _ in range(args.steps)]
+    tot = sum(times)
+    val = Bc * len(times) / tot
+    cores = os.cpu_count()
+    sample = "oracle port (numpy restatement of DiffLqr.apply+backward), B_cpu=%d per step, same n/m/T" % Bc
+    line = {"impl": "reference", "metric": "lqr_fwd_bwd_solves_per_sec", "value": val, "unit": "solves/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": desc, "n_state": n, "n_ctrl": m, "T": T, "batch_per_step": Bc},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+def make_problem_torch(torch, dev, n, m, T, B, seed):
+    """Synthetic random-stable dynamics, distinct per batch element."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    s = n + m
+    f64 = torch.float64
+    A = torch.eye(n, dtype=f64, device=dev) + 0.2 * torch.randn(B, n, n, dtype=f64, device=dev, generator=g)
+    rho = torch.linalg.eigvals(A).abs().amax(dim=1)
+    A = A * torch.clamp(0.95 / rho, max=1.0)[:, None, None]
+    Bm = torch.randn(B, n, m, dtype=f64, device=dev, generator=g)
+    Fb = torch.cat((A, Bm), dim=2)
+    F = Fb[None].expand(T - 1, B, n, s).contiguous()
+    L = 0.3 * torch.randn(B, s, s, dtype=f64, device=dev, generator=g)
+    Cb = L @ L.transpose(1, 2) + torch.eye(s, dtype=f64, device=dev)
+    C = Cb[None].expand(T, B, s, s).contiguous()
+    c = torch.randn(T, B, s, dtype=f64, device=dev, generator=g)
+    f = 0.1 * torch.randn(T - 1, B, n, dtype=f64, device=dev, generator=g)
+    x0 = torch.randn(B, n, dtype=f64, device=dev, generator=g)
+    gx = torch.randn(T, B, n, dtype=f64, device=dev, generator=g) / (T * B)
+    gu = torch.randn(T, B, m, dtype=f64, device=dev, generator=g) / (T * B)
+    return dict(x0=x0, C=C, c=c, F=F, f=f, gx=gx, gu=gu)
+
+
+def run_b200(args):
+    import torch
+    import _native
+    n, m, T, B, desc = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    s = n + m
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = _native.Context(local)
+    pr = make_problem_torch(torch, dev, n, m, T, B, seed=1234 + rank)
+    f64 = torch.float64
+    out = dict(x=torch.empty(T, B, n, dtype=f64, device=dev), u=torch.empty(T, B, m, dtype=f64, device=dev),
+               Ks=torch.empty(T, B, m, n, dtype=f64, device=dev), ks=torch.empty(T, B, m, dtype=f64, device=dev),
+               fac=torch.empty(T, B, m * m + n * m, dtype=f64, device=dev),
+               dx0=torch.empty(B, n, dtype=f64, device=dev), dC=torch.empty(T, B, s, s, dtype=f64, device=dev),
+               dc=torch.empty(T, B, s, dtype=f64, device=dev), dF=torch.empty(T - 1, B, n, s, dtype=f64, device=dev),
+               df=torch.empty(T - 1, B, n, dtype=f64, device=dev))
+    # a non-default torch stream: its handle is passed to the C ABI (NULL would mean the
+    # library's own stream) and the CUDA events below are recorded on the same stream
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    P = lambda t: t.data_ptr()
+
+    def fwd():
+        ctx.lqr_solve(np.float64, T, B, n, m, P(pr["x0"]), P(pr["C"]), P(pr["c"]), P(pr["F"]), T - 1, P(pr["f"]),
+                      P(out["x"]), P(out["u"]), P(out["Ks"]), P(out["ks"]), P(out["fac"]),
+                      _native.LQR_FACTOR | _native.LQR_ROLLOUT | _native.LQR_SAVE_FAC, stream)
+
+    def bwd():
+        ctx.lqr_adjoint(np.float64, T, B, n, m, P(pr["C"]), P(pr["c"]), P(pr["F"]), P(out["x"]), P(out["u"]),
+                        P(pr["gx"]), P(pr["gu"]), P(out["Ks"]), P(out["fac"]), P(out["dx0"]), P(out["dC"]),
+                        P(out["dc"]), P(out["dF"]), P(out["df"]), _native.ADJ_STRICT_REFERENCE, stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        fwd(); bwd()
+    barrier()
+    # per-kernel timing of the dominant kernels (events on the launching stream)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launches
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    k = 0
+    ev[0].record()
+    for _ in range(args.steps):
+        fwd(); ev[k + 1].record()
+        bwd(); ev[k + 2].record()
+        k += 2
+    t_end.record()
+    barrier()
+    launches = ctx.launches - l0
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    fwd_ms = np.mean([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)])
+    bwd_ms = np.mean([ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)])
+    if dist is not None:
+        tt = torch.tensor([ms_total], dtype=f64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # sanity: finite outputs (a fast wrong kernel is not done)
+    ok = bool(torch.isfinite(out["x"]).all().item() and torch.isfinite(out["dF"]).all().item())
+
+    line = None
+    if rank == 0:
+        fwd_b, tot_b = algorithmic_bytes(n, m, T)
+        peak, peak_src = measured_peaks()
+        # dominant kernel = lqr_solve_kernel (forward): algorithmic fwd bytes / its launch duration
+        dom_ms, dom_bytes, dom_name = (fwd_ms, fwd_b, "lqr_solve_kernel") if fwd_ms >= bwd_ms else (bwd_ms, tot_b - fwd_b, "lqr_dtau_kernel+adjoint_out_kernel")
+        achieved = B * dom_bytes / (dom_ms * 1e-3) / 1e9
+        whole = B * tot_b / (ms_step * 1e-3) / 1e9
+        line = {"metric": "lqr_fwd_bwd_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "desc": desc, "n_state": n, "n_ctrl": m, "T": T,
+                           "batch_per_gpu": B, "global_batch": B * world, "parallelism": "batch-sharded x%d" % world,
+                           "l2": "inputs (%.1f GB/GPU) larger than L2" % (B * fwd_b / 1e9), "finite_outputs": ok},
+                "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+                             "whole_step_achieved": whole, "whole_step_frac": whole / peak,
+                             "algorithmic_bytes_per_solve": {"fwd": fwd_b, "fwd_bwd": tot_b}},
+                "clocks": clocks, "gpu_launches": launches}
+
+    # ---- e2e through the public API with host buffers (rank-local chunk) -----------------
+    e2e = None
+    try:
+        e2e = run_e2e(args, torch, ctx, n, m, T, world, dist, dev, rank)
+    except Exception as ex:  # report, do not hide
+        e2e = {"value": None, "unit": "solves/s", "error": repr(ex)[:200]}
+    if rank == 0:
+        line["e2e"] = e2e
+        if world == 1 and not args.no_cpu:
+            Bc = cpu_sample_batch(n, m, T)
+            cpu_lqr_fwd_bwd(n, m, T, min(Bc, 32))
+            tcpu = min(cpu_lqr_fwd_bwd(n, m, T, Bc) for _ in range(2))
+            line["cpu_baseline"] = {"value": Bc / tcpu, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "oracle port of DiffLqr.apply+backward, B_cpu=%d, same n/m/T, best of 2" % Bc}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, ctx, n, m, T, world, dist, dev, rank):
+    """Same metric through the reference-facing API (DiffLqr.apply + .backward) with HOST
+    (pinned) numpy buffers: H2D of the inputs and D2H of x,u and all gradients are inside
+    the timed region.  Uses a chunk of the per-GPU batch per call (stated in the result)."""
+    import differentiable_lqr as dl
+    Be = args.e2e_batch
+    s = n + m
+    rs = np.random.RandomState(99 + rank)
+
+    def pinned(shape):
+        t = torch.empty(shape, dtype=torch.float64).pin_memory()
+        return t.numpy()
+    C = pinned((T, Be, s, s)); c = pinned((T, Be, s)); F = pinned((T - 1, Be, n, s)); f = pinned((T - 1, Be, n))
+    x0 = pinned((Be, n)); gx = pinned((T, Be, n)); gu = pinned((T, Be, m))
+    A = np.eye(n) + 0.2 * rs.randn(n, n)
+    A *= min(1.0, 0.95 / np.max(np.abs(np.linalg.eigvals(A))))
+    F[...] = np.concatenate((A, rs.randn(n, m)), axis=1)[None, None] + 0.01 * rs.randn(1, Be, n, s)
+    L = 0.3 * rs.randn(Be, s, s)
+    C[...] = (L @ L.transpose(0, 2, 1) + np.eye(s))[None]
+    c[...] = rs.randn(T, Be, s); f[...] = 0.1 * rs.randn(T - 1, Be, n); x0[...] = rs.randn(Be, n)
+    gx[...] = rs.randn(T, Be, n); gu[...] = rs.randn(T, Be, m)
+    h2d = sum(a.nbytes for a in (C, c, F, f, x0, gx, gu))
+    d2h = 8 * (T * Be * s + Be * n + T * Be * s * s + T * Be * s + (T - 1) * Be * n * s + (T - 1) * Be * n)
+    node = dl.DiffLqr(T, Be, n, m, device=ctx.device, pinned_outputs=True)
+
+    def step():
+        x, u = node.apply_numpy(x0, C, c, F, f)
+        return node.backward_numpy(gx, gu)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    reps = max(2, min(args.steps, 5))
+    for _ in range(reps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    return {"value": world * Be * reps / dt, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "batch_per_call": Be, "api": "DiffLqr.apply_numpy + backward_numpy (pinned host buffers)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
+    ap.add_argument("--e2e-batch", type=int, default=512)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+# tiny local copy of the numpy generator so bench.py does not import from tests/
+class _Local:
+    @staticmethod
+    def lqr_problem_np(seed, T, B, n, m):
+        rs = np.random.RandomState(seed)
+        s = n + m
+        A = np.eye(n) + 0.2 * rs.randn(B, n, n)
+        rho = np.max(np.abs(np.linalg.eigvals(A)), axis=1)
+        A *= np.minimum(1.0, 0.95 / rho)[:, None, None]
+        Fb = np.concatenate((A, rs.randn(B, n, m)), axis=2)
+        F = np.repeat(Fb[None], T - 1, axis=0)
+        L = 0.3 * rs.randn(B, s, s)
+        C = np.repeat((L @ L.transpose(0, 2, 1) + np.eye(s))[None], T, axis=0)
+        return dict(x0=rs.randn(B, n), C=C, c=rs.randn(T, B, s), F=F, f=0.1 * rs.randn(T - 1, B, n))
+
+
+sys.modules["tests_helpers_local"] = _Local
+
+if __name__ == "__main__":
+    main()
