@@ -44,6 +44,12 @@ SIGNATURES = {
     "dmpc_lqr_fac_elems": (_sz, [_i, _i, _i, _i]),
     "dmpc_lqr_solve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "dmpc_lqr_adjoint": (_i, [_vp, _i, _i, _i, _i, _i] + [_vp] * 14 + [_i, _vp]),
+    "dmpc_pnqp": (_i, [_vp, _i, _i, _i] + [_vp] * 5 + [_i, _i] + [_vp] * 7),
+    "dmpc_mpc_step_forward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i,
+                                   _vp, _vp, ctypes.POINTER(_d), _d, _i, _i, _i] + [_vp] * 14),
+    "dmpc_mpc_step_backward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i] + [_vp] * 15 + [_vp]),
+    "dmpc_lqr_active_solve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dmpc_get_traj": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(_d), _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -188,6 +194,40 @@ class Context:
         self._check(self.lib.dmpc_lqr_adjoint(self.h, dtype_code(dtype), T, B, n, m, _p(C), _p(c), _p(F), _p(x), _p(u),
                                               _p(gx), _p(gu), _p(Ks), _p(fac), _p(dx0), _p(dC), _p(dc), _p(dF),
                                               _p(df), flags, stream))
+
+    def pnqp(self, dtype, B, m, H, q, lower, upper, x_init, x, LU, piv, free, iters, flags=None, n_iter=20,
+             coupling=COUPLING_ELEMENT, stream=None):
+        self._check(self.lib.dmpc_pnqp(self.h, dtype_code(dtype), B, m, _p(H), _p(q), _p(lower), _p(upper), _p(x_init),
+                                       n_iter, coupling, _p(x), _p(LU), _p(piv), _p(free), _p(iters), _p(flags), stream))
+
+    @staticmethod
+    def _dynp(params):
+        arr = (ctypes.c_double * 5)(*([float(v) for v in params] + [0.0] * (5 - len(params)))) if params is not None else None
+        return arr
+
+    def mpc_step_forward(self, dtype, T, B, n, m, C, c, F, F_T, f, x_nom, u_nom, lower, upper, tC, tc, dynamics, tF,
+                         tf, dyn_params, ls_decay, max_ls_trials, need_expand, coupling, x, u, Ks, ks, u_first, objs,
+                         costs, old_costs, alphas, n_qp, free, n_ls, flags, stream=None):
+        self._check(self.lib.dmpc_mpc_step_forward(
+            self.h, dtype_code(dtype), T, B, n, m, _p(C), _p(c), _p(F), F_T, _p(f), _p(x_nom), _p(u_nom), _p(lower),
+            _p(upper), _p(tC), _p(tc), dynamics, _p(tF), _p(tf), self._dynp(dyn_params), float(ls_decay),
+            int(max_ls_trials), int(bool(need_expand)), coupling, _p(x), _p(u), _p(Ks), _p(ks), _p(u_first), _p(objs),
+            _p(costs), _p(old_costs), _p(alphas), _p(n_qp), _p(free), _p(n_ls), _p(flags), stream))
+
+    def mpc_step_backward(self, dtype, T, B, n, m, C, c, F, F_T, x, u, lower, upper, gx, gu, ws_Ks, ws_ks, ws_dtau,
+                          active, dx0, dC, dc, dF, df, stream=None):
+        self._check(self.lib.dmpc_mpc_step_backward(
+            self.h, dtype_code(dtype), T, B, n, m, _p(C), _p(c), _p(F), F_T, _p(x), _p(u), _p(lower), _p(upper),
+            _p(gx), _p(gu), _p(ws_Ks), _p(ws_ks), _p(ws_dtau), _p(active), _p(dx0), _p(dC), _p(dc), _p(dF), _p(df),
+            stream))
+
+    def lqr_active_solve(self, dtype, T, B, n, m, x0, C, c, F, F_T, f, active, x, u, Ks, ks, stream=None):
+        self._check(self.lib.dmpc_lqr_active_solve(self.h, dtype_code(dtype), T, B, n, m, _p(x0), _p(C), _p(c), _p(F),
+                                                   F_T, _p(f), _p(active), _p(x), _p(u), _p(Ks), _p(ks), stream))
+
+    def get_traj(self, dtype, T, B, n, m, dynamics, x0, u, F, f, dyn_params, x, Fout=None, fout=None, stream=None):
+        self._check(self.lib.dmpc_get_traj(self.h, dtype_code(dtype), T, B, n, m, dynamics, _p(x0), _p(u), _p(F), _p(f),
+                                           self._dynp(dyn_params), _p(x), _p(Fout), _p(fout), stream))
 
     def lqr_fac_elems(self, T, B, n, m):
         return int(self.lib.dmpc_lqr_fac_elems(T, B, n, m))

@@ -4,6 +4,7 @@
 #include <string>
 #include "../../include/diffmpc_b200.h"
 #include "launch.h"
+#include "mpc_launch.h"
 
 struct dmpc_ctx {
   int device = 0;
@@ -67,6 +68,105 @@ static int lqr_adjoint_impl(dmpc_handle h, int T, int B, int n, int m, const voi
   a.dx0 = (R*)dx0; a.dC = (R*)dC; a.dc = (R*)dc; a.dF = (R*)dF; a.df = (R*)df;
   rc = launch_adjoint_out<R>(a, st, &h->launches);
   if (rc) h->err = "adjoint_out launch failed";
+  return rc;
+}
+
+
+template <typename R>
+static int mpc_forward_impl(dmpc_handle h, int T, int B, int n, int m, const void* C, const void* c, const void* F,
+                            int F_T, const void* f, const void* x_nom, const void* u_nom, const void* lo,
+                            const void* hi, const void* tC, const void* tc, int dynamics, const void* tF,
+                            const void* tf, const double* dynp, double ls_decay, int max_ls_trials, int need_expand,
+                            int coupling, void* x, void* u, void* Ks, void* ks, void* u_first, void* objs,
+                            void* costs, void* old_costs, void* alphas, void* n_qp, void* free_m, void* n_ls,
+                            void* flags, cudaStream_t st) {
+  MpcFwdParams<R> p;
+  memset(&p, 0, sizeof(p));
+  p.T = T; p.B = B; p.n = n; p.m = m; p.F_T = F_T; p.need_expand = need_expand; p.dynamics = dynamics;
+  p.coupling = coupling; p.max_ls_trials = max_ls_trials > 0 ? max_ls_trials : 64; p.n_qp_iter = 20;
+  p.ls_decay = (R)ls_decay;
+  p.C = (const R*)C; p.c = (const R*)c; p.F = (const R*)F; p.f = (const R*)f;
+  p.x_nom = (const R*)x_nom; p.u_nom = (const R*)u_nom; p.lo = (const R*)lo; p.hi = (const R*)hi;
+  p.tC = (const R*)tC; p.tc = (const R*)tc; p.tF = (const R*)tF; p.tf = (const R*)tf;
+  for (int i = 0; i < 5; ++i) p.dyn_params[i] = dynp ? (R)dynp[i < 3 ? i : i] : R(0);
+  p.x = (R*)x; p.u = (R*)u; p.Ks = (R*)Ks; p.ks = (R*)ks; p.u_first = (R*)u_first; p.objs = (R*)objs;
+  p.costs = (R*)costs; p.old_costs = (R*)old_costs; p.alphas = (R*)alphas; p.n_qp = (int*)n_qp;
+  p.free_mask = (unsigned char*)free_m; p.n_ls = (int*)n_ls; p.flags = (int*)flags;
+  int rc = launch_mpc_forward<R>(p, st, &h->launches);
+  if (rc) h->err = rc == DMPC_ERR_UNSUPPORTED ? "mpc_step_forward: unsupported shape / batch coupling needs the batch in one CTA" : "mpc_step_forward launch failed";
+  return rc;
+}
+
+template <typename R>
+static int mpc_backward_impl(dmpc_handle h, int T, int B, int n, int m, const void* C, const void* c, const void* F,
+                             int F_T, const void* x, const void* u, const void* lo, const void* hi, const void* gx,
+                             const void* gu, void* wsK, void* wsk, void* wsd, void* act, void* dx0, void* dC,
+                             void* dc, void* dF, void* df, cudaStream_t st) {
+  int rc = launch_active_mask<R>((const R*)u, (const R*)lo, (const R*)hi, (unsigned char*)act, (size_t)T * B * m, st, &h->launches);
+  if (rc) { h->err = "active_mask launch failed"; return rc; }
+  if (cudaMemsetAsync(dx0, 0, (size_t)B * n * sizeof(R), st) != cudaSuccess) return DMPC_ERR_CUDA;
+  LqrParams<R> p;
+  memset(&p, 0, sizeof(p));
+  p.T = T; p.B = B; p.n = n; p.m = m;
+  p.flags = LQR_DO_FACTOR | LQR_DO_ROLLOUT | LQR_MASKED;
+  p.x0 = (const R*)dx0;                       // zeros (mpc_step.py:365)
+  p.C = (const R*)C; p.c = nullptr; p.cx = (const R*)gx; p.cu = (const R*)gu; p.c_scale = R(-1);   // c := -d_taus (:374)
+  p.F = (const R*)F; p.f = nullptr; p.active = (const unsigned char*)act;
+  p.Ks = (R*)wsK; p.ks = (R*)wsk; p.tau_out = (R*)wsd;
+  rc = launch_lqr_solve<R>(p, st, &h->launches);
+  if (rc) { h->err = "lqr_active launch failed"; return rc; }
+  AdjOutParams<R> a;
+  memset(&a, 0, sizeof(a));
+  a.T = T; a.B = B; a.n = n; a.m = m; a.F_T = F_T;
+  a.flags = ADJ_NEGATE | ADJ_NEG_RHS;
+  a.C = (const R*)C; a.c = (const R*)c; a.F = (const R*)F; a.x = (const R*)x; a.u = (const R*)u;
+  a.dtau = (const R*)wsd; a.gx = (const R*)gx; a.gu = (const R*)gu;
+  a.dx0 = (R*)dx0; a.dC = (R*)dC; a.dc = (R*)dc; a.dF = (R*)dF; a.df = (R*)df;
+  rc = launch_adjoint_out<R>(a, st, &h->launches);
+  if (rc) h->err = "adjoint_out launch failed";
+  return rc;
+}
+
+template <typename R>
+static int lqr_active_impl(dmpc_handle h, int T, int B, int n, int m, const void* x0, const void* C, const void* c,
+                           const void* F, const void* f, const void* act, void* x, void* u, void* Ks, void* ks,
+                           cudaStream_t st) {
+  LqrParams<R> p;
+  memset(&p, 0, sizeof(p));
+  p.T = T; p.B = B; p.n = n; p.m = m;
+  p.flags = LQR_DO_FACTOR | LQR_DO_ROLLOUT | LQR_MASKED;
+  p.x0 = (const R*)x0; p.C = (const R*)C; p.c = (const R*)c; p.c_scale = R(1); p.F = (const R*)F; p.f = (const R*)f;
+  p.active = (const unsigned char*)act; p.x = (R*)x; p.u = (R*)u; p.Ks = (R*)Ks; p.ks = (R*)ks;
+  int rc = launch_lqr_solve<R>(p, st, &h->launches);
+  if (rc) h->err = "lqr_active launch failed";
+  return rc;
+}
+
+template <typename R>
+static int pnqp_impl(dmpc_handle h, int B, int m, const void* H, const void* q, const void* lo, const void* hi,
+                     const void* xi, int n_iter, int coupling, void* x, void* LU, void* piv, void* fr, void* it,
+                     void* fl, cudaStream_t st) {
+  PnqpParams<R> p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.m = m; p.n_iter = n_iter; p.coupling = coupling;
+  p.H = (const R*)H; p.q = (const R*)q; p.lo = (const R*)lo; p.hi = (const R*)hi; p.x_init = (const R*)xi;
+  p.x = (R*)x; p.LU = (R*)LU; p.piv = (int*)piv; p.free_out = (R*)fr; p.iters = (int*)it; p.flags = (int*)fl;
+  int rc = launch_pnqp<R>(p, st, &h->launches);
+  if (rc) h->err = rc == DMPC_ERR_UNSUPPORTED ? "pnqp: unsupported (m > 32, or batch coupling with the batch not in one CTA)" : "pnqp launch failed";
+  return rc;
+}
+
+template <typename R>
+static int traj_impl(dmpc_handle h, int T, int B, int n, int m, int dynamics, const void* x0, const void* u,
+                     const void* F, const void* f, const double* dynp, void* x, void* Fo, void* fo, cudaStream_t st) {
+  TrajParams<R> p;
+  memset(&p, 0, sizeof(p));
+  p.T = T; p.B = B; p.n = n; p.m = m; p.dynamics = dynamics;
+  p.x0 = (const R*)x0; p.u = (const R*)u; p.F = (const R*)F; p.f = (const R*)f;
+  for (int i = 0; i < 5; ++i) p.dyn_params[i] = dynp ? (R)dynp[i] : R(0);
+  p.x = (R*)x; p.Fout = (R*)Fo; p.fout = (R*)fo;
+  int rc = launch_traj<R>(p, st, &h->launches);
+  if (rc) h->err = "get_traj launch failed";
   return rc;
 }
 
@@ -197,6 +297,90 @@ int dmpc_lqr_adjoint(dmpc_handle h, int dtype, int T, int B, int n, int m, const
   cudaStream_t st = pick(h, stream);
   if (dtype == DMPC_F64) return lqr_adjoint_impl<double>(h, T, B, n, m, d_C, d_c, d_F, d_x, d_u, d_gx, d_gu, d_Ks, d_fac, d_dx0, d_dC, d_dc, d_dF, d_df, flags, st);
   if (dtype == DMPC_F32) return lqr_adjoint_impl<float>(h, T, B, n, m, d_C, d_c, d_F, d_x, d_u, d_gx, d_gu, d_Ks, d_fac, d_dx0, d_dC, d_dc, d_dF, d_df, flags, st);
+  return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
+}
+
+int dmpc_pnqp(dmpc_handle h, int dtype, int B, int m, const void* d_H, const void* d_q, const void* d_lower,
+              const void* d_upper, const void* d_x_init, int n_iter, int coupling, void* d_x, void* d_LU,
+              void* d_piv, void* d_free, void* d_iters, void* d_flags, void* stream) {
+  if (!h) return DMPC_ERR_NULL;
+  if (B < 1 || m < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "B,m must be >= 1");
+  if (!d_H || !d_q || !d_lower || !d_upper || !d_x || !d_free || !d_iters) return fail(h, DMPC_ERR_NULL, "pnqp: required buffer is NULL");
+  if (set_dev(h)) return DMPC_ERR_CUDA;
+  cudaStream_t st = pick(h, stream);
+  if (dtype == DMPC_F64) return pnqp_impl<double>(h, B, m, d_H, d_q, d_lower, d_upper, d_x_init, n_iter, coupling, d_x, d_LU, d_piv, d_free, d_iters, d_flags, st);
+  if (dtype == DMPC_F32) return pnqp_impl<float>(h, B, m, d_H, d_q, d_lower, d_upper, d_x_init, n_iter, coupling, d_x, d_LU, d_piv, d_free, d_iters, d_flags, st);
+  return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
+}
+
+int dmpc_mpc_step_forward(dmpc_handle h, int dtype, int T, int B, int n, int m, const void* d_C, const void* d_c,
+                          const void* d_F, int F_T, const void* d_f, const void* d_x_nom, const void* d_u_nom,
+                          const void* d_lower, const void* d_upper, const void* d_tC, const void* d_tc, int dynamics,
+                          const void* d_tF, const void* d_tf, const double* h_dyn_params, double ls_decay,
+                          int max_ls_trials, int need_expand, int coupling, void* d_x, void* d_u, void* d_Ks,
+                          void* d_ks, void* d_u_first, void* d_objs, void* d_costs, void* d_old_costs, void* d_alphas,
+                          void* d_n_qp, void* d_free, void* d_n_ls, void* d_flags, void* stream) {
+  if (!h) return DMPC_ERR_NULL;
+  if (T < 1 || B < 1 || n < 1 || m < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "T,B,n,m must be >= 1");
+  if (T > 1 && F_T != T - 1 && F_T != T) return fail(h, DMPC_ERR_BAD_SHAPE, "F_hat must have T-1 or T time rows");
+  if (!d_C || !d_c || (T > 1 && !d_F) || !d_x_nom || !d_u_nom || !d_lower || !d_upper || !d_tC || !d_tc || !d_x || !d_u ||
+      !d_Ks || !d_ks || !d_costs || !d_alphas)
+    return fail(h, DMPC_ERR_NULL, "mpc_step_forward: required buffer is NULL");
+  if (dynamics == DMPC_DYN_LINEAR && T > 1 && !d_tF) return fail(h, DMPC_ERR_NULL, "linear true dynamics need d_tF");
+  if (dynamics == DMPC_DYN_PENDULUM && (n != 3 || m != 1 || !h_dyn_params)) return fail(h, DMPC_ERR_BAD_SHAPE, "pendulum dynamics: n=3, m=1, params required");
+  if (dynamics != DMPC_DYN_LINEAR && dynamics != DMPC_DYN_PENDULUM) return fail(h, DMPC_ERR_UNSUPPORTED, "dynamics selector");
+  if (set_dev(h)) return DMPC_ERR_CUDA;
+  cudaStream_t st = pick(h, stream);
+  if (dtype == DMPC_F64) return mpc_forward_impl<double>(h, T, B, n, m, d_C, d_c, d_F, F_T, d_f, d_x_nom, d_u_nom, d_lower, d_upper, d_tC, d_tc, dynamics, d_tF, d_tf, h_dyn_params, ls_decay, max_ls_trials, need_expand, coupling, d_x, d_u, d_Ks, d_ks, d_u_first, d_objs, d_costs, d_old_costs, d_alphas, d_n_qp, d_free, d_n_ls, d_flags, st);
+  if (dtype == DMPC_F32) return mpc_forward_impl<float>(h, T, B, n, m, d_C, d_c, d_F, F_T, d_f, d_x_nom, d_u_nom, d_lower, d_upper, d_tC, d_tc, dynamics, d_tF, d_tf, h_dyn_params, ls_decay, max_ls_trials, need_expand, coupling, d_x, d_u, d_Ks, d_ks, d_u_first, d_objs, d_costs, d_old_costs, d_alphas, d_n_qp, d_free, d_n_ls, d_flags, st);
+  return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
+}
+
+int dmpc_mpc_step_backward(dmpc_handle h, int dtype, int T, int B, int n, int m, const void* d_C, const void* d_c,
+                           const void* d_F, int F_T, const void* d_x, const void* d_u, const void* d_lower,
+                           const void* d_upper, const void* d_gx, const void* d_gu, void* d_ws_Ks, void* d_ws_ks,
+                           void* d_ws_dtau, void* d_active, void* d_dx0, void* d_dC, void* d_dc, void* d_dF,
+                           void* d_df, void* stream) {
+  if (!h) return DMPC_ERR_NULL;
+  if (T < 1 || B < 1 || n < 1 || m < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "T,B,n,m must be >= 1");
+  if (T > 1 && F_T != T - 1 && F_T != T) return fail(h, DMPC_ERR_BAD_SHAPE, "F_hat must have T-1 or T time rows");
+  if (!d_C || !d_c || (T > 1 && (!d_F || !d_dF)) || !d_x || !d_u || !d_lower || !d_upper || !d_ws_Ks || !d_ws_ks || !d_ws_dtau ||
+      !d_active || !d_dx0 || !d_dC || !d_dc)
+    return fail(h, DMPC_ERR_NULL, "mpc_step_backward: required buffer is NULL");
+  if (set_dev(h)) return DMPC_ERR_CUDA;
+  cudaStream_t st = pick(h, stream);
+  if (dtype == DMPC_F64) return mpc_backward_impl<double>(h, T, B, n, m, d_C, d_c, d_F, F_T, d_x, d_u, d_lower, d_upper, d_gx, d_gu, d_ws_Ks, d_ws_ks, d_ws_dtau, d_active, d_dx0, d_dC, d_dc, d_dF, d_df, st);
+  if (dtype == DMPC_F32) return mpc_backward_impl<float>(h, T, B, n, m, d_C, d_c, d_F, F_T, d_x, d_u, d_lower, d_upper, d_gx, d_gu, d_ws_Ks, d_ws_ks, d_ws_dtau, d_active, d_dx0, d_dC, d_dc, d_dF, d_df, st);
+  return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
+}
+
+int dmpc_lqr_active_solve(dmpc_handle h, int dtype, int T, int B, int n, int m, const void* d_x0, const void* d_C,
+                          const void* d_c, const void* d_F, int F_T, const void* d_f, const void* d_active, void* d_x,
+                          void* d_u, void* d_Ks, void* d_ks, void* stream) {
+  if (!h) return DMPC_ERR_NULL;
+  if (T < 1 || B < 1 || n < 1 || m < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "T,B,n,m must be >= 1");
+  if (T > 1 && F_T != T - 1 && F_T != T) return fail(h, DMPC_ERR_BAD_SHAPE, "F must have T-1 or T time rows");
+  if (!d_x0 || !d_C || !d_c || (T > 1 && !d_F) || !d_active || !d_x || !d_u || !d_Ks || !d_ks) return fail(h, DMPC_ERR_NULL, "lqr_active: required buffer is NULL");
+  if (set_dev(h)) return DMPC_ERR_CUDA;
+  cudaStream_t st = pick(h, stream);
+  if (dtype == DMPC_F64) return lqr_active_impl<double>(h, T, B, n, m, d_x0, d_C, d_c, d_F, d_f, d_active, d_x, d_u, d_Ks, d_ks, st);
+  if (dtype == DMPC_F32) return lqr_active_impl<float>(h, T, B, n, m, d_x0, d_C, d_c, d_F, d_f, d_active, d_x, d_u, d_Ks, d_ks, st);
+  return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
+}
+
+int dmpc_get_traj(dmpc_handle h, int dtype, int T, int B, int n, int m, int dynamics, const void* d_x0,
+                  const void* d_u, const void* d_F, const void* d_f, const double* h_dyn_params, void* d_x,
+                  void* d_Fout, void* d_fout, void* stream) {
+  if (!h) return DMPC_ERR_NULL;
+  if (T < 1 || B < 1 || n < 1 || m < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "T,B,n,m must be >= 1");
+  if (!d_x0 || !d_u || !d_x) return fail(h, DMPC_ERR_NULL, "get_traj: required buffer is NULL");
+  if (dynamics == DMPC_DYN_LINEAR && T > 1 && !d_F) return fail(h, DMPC_ERR_NULL, "linear dynamics need d_F");
+  if (dynamics == DMPC_DYN_PENDULUM && (n != 3 || m != 1 || !h_dyn_params)) return fail(h, DMPC_ERR_BAD_SHAPE, "pendulum dynamics: n=3, m=1, params required");
+  if ((d_Fout == nullptr) != (d_fout == nullptr)) return fail(h, DMPC_ERR_NULL, "Fout and fout go together");
+  if (set_dev(h)) return DMPC_ERR_CUDA;
+  cudaStream_t st = pick(h, stream);
+  if (dtype == DMPC_F64) return traj_impl<double>(h, T, B, n, m, dynamics, d_x0, d_u, d_F, d_f, h_dyn_params, d_x, d_Fout, d_fout, st);
+  if (dtype == DMPC_F32) return traj_impl<float>(h, T, B, n, m, dynamics, d_x0, d_u, d_F, d_f, h_dyn_params, d_x, d_Fout, d_fout, st);
   return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
 }
 

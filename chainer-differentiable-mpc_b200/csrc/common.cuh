@@ -21,6 +21,17 @@ enum ElemFlag : int {
   FLAG_LS_CAPPED = DMPC_FLAG_LS_CAPPED,
 };
 
+// ---------------------------------------------------------------- pinned arithmetic
+// Explicitly rounded operations: the compiler may neither contract nor re-associate them, so a
+// rollout re-evaluated in another kernel reproduces the first one bit for bit (the line search
+// relies on cost(alpha -> 0) == cost(nominal), mpc_step.py:196).
+__device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
 // ---------------------------------------------------------------- groups
 template <int G>
 struct Grp {

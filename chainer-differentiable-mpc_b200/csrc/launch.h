@@ -8,7 +8,6 @@ namespace dmpc {
 // Which (n, m) shapes have compile-time-specialised kernels (everything else runs the
 // runtime-shape instantiation of the same code).
 struct ShapeInfo { int n, m, G; bool specialised; };
-ShapeInfo pick_shape(int n, int m);
 
 template <typename R> int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nlaunch);
 template <typename R> int launch_lqr_dtau(const DtauParams<R>& p, cudaStream_t st, long long* nlaunch);

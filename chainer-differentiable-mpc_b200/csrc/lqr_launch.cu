@@ -1,13 +1,17 @@
 // Kernel instantiation + shape dispatch for the LQR kernels (lqr_kernels.cuh).
 #include "launch.h"
 
+#ifndef DMPC_REAL
+#define DMPC_REAL double
+#endif
+
 namespace dmpc {
 
 // Compile-time shapes: the BASELINE.json configs + the reference's examples.
 //   (3,1) pendulum / Boyd / LQRnet   (2,1) one-variable example   (4,2) c2   (8,4) c3   (32,8) c5
 #define DMPC_SHAPES(X) X(2, 1, 4) X(3, 1, 4) X(4, 2, 8) X(8, 4, 16) X(32, 8, 256)
 
-ShapeInfo pick_shape(int n, int m) {
+inline ShapeInfo pick_shape_impl(int n, int m) {
 #define X(N_, M_, G_) if (n == N_ && m == M_) return ShapeInfo{N_, M_, G_, true};
   DMPC_SHAPES(X)
 #undef X
@@ -37,7 +41,7 @@ static int do_launch(K kernel, const P& p, int G, size_t stride_bytes, int B, cu
 
 template <typename R>
 int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
-  const ShapeInfo si = pick_shape(p.n, p.m);
+  const ShapeInfo si = pick_shape_impl(p.n, p.m);
   const LqrLayout L = lqr_layout<R>(p.n, p.m, (p.flags & LQR_SAVE_FAC) != 0);
   const size_t sb = (size_t)L.stride * sizeof(R);
 #define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) return do_launch(lqr_solve_kernel<R, N_, M_, G_>, p, G_, sb, p.B, st, nl);
@@ -54,7 +58,7 @@ int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
 
 template <typename R>
 int launch_lqr_dtau(const DtauParams<R>& p, cudaStream_t st, long long* nl) {
-  const ShapeInfo si = pick_shape(p.n, p.m);
+  const ShapeInfo si = pick_shape_impl(p.n, p.m);
   const DtauLayout L = dtau_layout<R>(p.n, p.m);
   const size_t sb = (size_t)L.stride * sizeof(R);
 #define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) return do_launch(lqr_dtau_kernel<R, N_, M_, (G_ > 32 ? 64 : G_)>, p, (G_ > 32 ? 64 : G_), sb, p.B, st, nl);
@@ -70,7 +74,7 @@ int launch_lqr_dtau(const DtauParams<R>& p, cudaStream_t st, long long* nl) {
 
 template <typename R>
 int launch_adjoint_out(const AdjOutParams<R>& p, cudaStream_t st, long long* nl) {
-  const ShapeInfo si = pick_shape(p.n, p.m);
+  const ShapeInfo si = pick_shape_impl(p.n, p.m);
   const AdjLayout L = adj_layout<R>(p.n, p.m);
   const size_t sb = (size_t)L.stride * sizeof(R);
 #define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) return do_launch(adjoint_out_kernel<R, N_, M_, (G_ > 32 ? 128 : G_)>, p, (G_ > 32 ? 128 : G_), sb, p.B, st, nl);
@@ -84,11 +88,10 @@ int launch_adjoint_out(const AdjOutParams<R>& p, cudaStream_t st, long long* nl)
   }
 }
 
-template int launch_lqr_solve<double>(const LqrParams<double>&, cudaStream_t, long long*);
-template int launch_lqr_solve<float>(const LqrParams<float>&, cudaStream_t, long long*);
-template int launch_lqr_dtau<double>(const DtauParams<double>&, cudaStream_t, long long*);
-template int launch_lqr_dtau<float>(const DtauParams<float>&, cudaStream_t, long long*);
-template int launch_adjoint_out<double>(const AdjOutParams<double>&, cudaStream_t, long long*);
-template int launch_adjoint_out<float>(const AdjOutParams<float>&, cudaStream_t, long long*);
+template int launch_lqr_solve<DMPC_REAL>(const LqrParams<DMPC_REAL>&, cudaStream_t, long long*);
+template int launch_lqr_dtau<DMPC_REAL>(const DtauParams<DMPC_REAL>&, cudaStream_t, long long*);
+template int launch_adjoint_out<DMPC_REAL>(const AdjOutParams<DMPC_REAL>&, cudaStream_t, long long*);
 
+#ifdef DMPC_DEFINE_PICK_SHAPE
+#endif
 }  // namespace dmpc

@@ -1,0 +1,104 @@
+// Kernel instantiation + shape dispatch for the MPC kernels (mpc_kernels.cuh).
+// Compiled once per dtype (-DDMPC_REAL=double|float) so the two builds run in parallel.
+#include "launch.h"
+#include "mpc_kernels.cuh"
+#include "mpc_launch.h"
+
+#ifndef DMPC_REAL
+#define DMPC_REAL double
+#endif
+
+namespace dmpc {
+
+typedef DMPC_REAL Rr;
+
+template <typename K, typename P>
+static int launch_elems(K kernel, const P& p, int G, size_t stride_bytes, int B, bool one_cta, cudaStream_t st,
+                        long long* nl) {
+  int tpb, epb;
+  if (G > 32) { tpb = G; epb = 1; }
+  else if (one_cta) {
+    tpb = ((B * G + 31) / 32) * 32;
+    if (tpb > 1024) return DMPC_ERR_UNSUPPORTED;   // batch coupling needs the whole batch in one CTA
+    epb = tpb / G;                                 // padded groups replicate element B-1 in their own region
+  } else {
+    tpb = 128; epb = tpb / G;
+    while ((size_t)epb * stride_bytes > (size_t)kMaxSmem && tpb > 32) { tpb /= 2; epb = tpb / G; }
+    while (tpb > 32 && (B + epb - 1) / epb < 148 * 2) { tpb /= 2; epb = tpb / G; }
+  }
+  const size_t smem = (size_t)epb * stride_bytes;
+  if (smem > (size_t)kMaxSmem) return DMPC_ERR_UNSUPPORTED;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DMPC_ERR_CUDA;
+  const int grid = one_cta ? 1 : (B + epb - 1) / epb;
+  kernel<<<grid, tpb, smem, st>>>(p);
+  if (nl) ++*nl;
+  return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+}
+
+#define MPC_SHAPES(X) X(3, 1, 4) X(4, 2, 8) X(8, 4, 16)
+
+template <>
+int launch_mpc_forward<Rr>(const MpcFwdParams<Rr>& p, cudaStream_t st, long long* nl) {
+  const MpcLayout L = mpc_layout<Rr>(p.n, p.m);
+  const size_t sb = (size_t)L.stride * sizeof(Rr);
+  const bool batch = p.coupling == DMPC_COUPLING_BATCH;
+  if (p.m > 32) return DMPC_ERR_UNSUPPORTED;
+#define X(N_, M_, G_)                                                                                              \
+  if (p.n == N_ && p.m == M_) {                                                                                    \
+    if (batch) return launch_elems(mpc_forward_kernel<Rr, N_, M_, G_, true>, p, G_, sb, p.B, true, st, nl);        \
+    return launch_elems(mpc_forward_kernel<Rr, N_, M_, G_, false>, p, G_, sb, p.B, false, st, nl);                 \
+  }
+  MPC_SHAPES(X)
+#undef X
+  const int s = p.n + p.m;
+  if (s <= 6 && p.m <= 8) {
+    if (batch) return launch_elems(mpc_forward_kernel<Rr, 0, 0, 8, true>, p, 8, sb, p.B, true, st, nl);
+    return launch_elems(mpc_forward_kernel<Rr, 0, 0, 8, false>, p, 8, sb, p.B, false, st, nl);
+  }
+  if (s <= 14 && p.m <= 16) {
+    if (batch) return launch_elems(mpc_forward_kernel<Rr, 0, 0, 16, true>, p, 16, sb, p.B, true, st, nl);
+    return launch_elems(mpc_forward_kernel<Rr, 0, 0, 16, false>, p, 16, sb, p.B, false, st, nl);
+  }
+  if (s <= 24) {
+    if (batch) return launch_elems(mpc_forward_kernel<Rr, 0, 0, 32, true>, p, 32, sb, p.B, true, st, nl);
+    return launch_elems(mpc_forward_kernel<Rr, 0, 0, 32, false>, p, 32, sb, p.B, false, st, nl);
+  }
+  if (batch) return DMPC_ERR_UNSUPPORTED;
+  return launch_elems(mpc_forward_kernel<Rr, 0, 0, 256, false>, p, 256, sb, p.B, false, st, nl);
+}
+
+template <>
+int launch_pnqp<Rr>(const PnqpParams<Rr>& p, cudaStream_t st, long long* nl) {
+  const bool batch = p.coupling == DMPC_COUPLING_BATCH;
+  const size_t sb = (size_t)pnqp_stride<Rr>(p.m) * sizeof(Rr);
+  if (p.m > 32) return DMPC_ERR_UNSUPPORTED;
+  const int SG = p.m <= 4 ? 4 : (p.m <= 8 ? 8 : (p.m <= 16 ? 16 : 32));
+#define PN(SG_)                                                                                      \
+  if (SG == SG_) {                                                                                   \
+    if (batch) return launch_elems(pnqp_kernel<Rr, 0, SG_, true>, p, SG_, sb, p.B, true, st, nl);    \
+    return launch_elems(pnqp_kernel<Rr, 0, SG_, false>, p, SG_, sb, p.B, false, st, nl);             \
+  }
+  PN(4) PN(8) PN(16) PN(32)
+#undef PN
+  return DMPC_ERR_UNSUPPORTED;
+}
+
+template <>
+int launch_active_mask<Rr>(const Rr* u, const Rr* lo, const Rr* hi, unsigned char* out, size_t count, cudaStream_t st,
+                           long long* nl) {
+  const int tpb = 256;
+  active_mask_kernel<Rr><<<(unsigned)((count + tpb - 1) / tpb), tpb, 0, st>>>(u, lo, hi, out, count);
+  if (nl) ++*nl;
+  return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+}
+
+template <>
+int launch_traj<Rr>(const TrajParams<Rr>& p, cudaStream_t st, long long* nl) {
+  if (p.n + p.m > 64) return DMPC_ERR_UNSUPPORTED;
+  const int tpb = 64;
+  traj_kernel<Rr, 64><<<(p.B + tpb - 1) / tpb, tpb, 0, st>>>(p);
+  if (nl) ++*nl;
+  return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+}
+
+}  // namespace dmpc

@@ -1,0 +1,205 @@
+"""MPCstep on B200 - one box-DDP / iLQR step as a FunctionNode, API of reference mpc/mpc_step.py:33-460.
+
+forward  (reference :288-328): Taylor shift + bounded Riccati sweep with one PNQP per timestep +
+          line search through the true dynamics/cost - ONE kernel launch (`mpc_forward_kernel`).
+backward (reference :330-460): active-set LQR (LQR_active) + lambda/d-lambda recursions + outer
+          products - three launches (`dmpc_mpc_step_backward`).
+
+Supported true_cost: util.QuadCost.  Supported true_dynamics: util.LinDx, or a pendulum object
+(the reference's env_dx.pendulum.PendulumDx or pendulum_dx.PendulumDx of this package), whose step
+and analytic Jacobian are device code.  Other Python callables cannot run inside a fused kernel
+and raise NotImplementedError.
+
+The batch-scrambled `full_du_norm` / `alpha_du_norm` (reference :261-263, :275-277) are reproduced
+bit-faithfully on the host from the kernel's alpha=1 controls.
+"""
+import os
+import sys
+import warnings
+from collections import namedtuple
+
+_here = os.path.dirname(os.path.abspath(__file__))
+_pkg = os.path.dirname(_here)
+for _p in (_pkg, _here, os.path.join(_pkg, "lqr")):
+    if _p not in sys.path:
+        sys.path.append(_p)
+
+import numpy as np  # noqa: E402
+
+import _native  # noqa: E402
+from _compat import FunctionNodeBase, to_xp, wrap, as_f  # noqa: E402
+from util import QuadCost, LinDx  # noqa: E402
+
+LqrBackOut = namedtuple("lqrBackOut", "n_total_qp_iter")
+LqrForOut = namedtuple("lqrForOut", "objs full_du_norm alpha_du_norm mean_alphas costs")
+
+DEFAULT_COUPLING = "auto"     # 'batch' | 'element' | 'auto' (see pnqp.py)
+MAX_LS_TRIALS = 64            # safety cap of the per-element line search (reference has none, Q5)
+
+
+def is_pendulum(dyn):
+    return type(dyn).__name__ == "PendulumDx" or getattr(dyn, "_dmpc_dynamics", None) == "pendulum"
+
+
+def pendulum_params(dyn):
+    if hasattr(dyn, "simple") and not dyn.simple:
+        raise NotImplementedError("only the `simple` pendulum model (g, m, l) has device code")
+    p = np.asarray(to_xp(dyn.params), dtype=np.float64).ravel()
+    return (float(p[0]), float(p[1]), float(p[2]))
+
+
+def _group_size(n, m):
+    table = {(3, 1): 4, (4, 2): 8, (8, 4): 16}
+    if (n, m) in table:
+        return table[(n, m)]
+    s = n + m
+    return 8 if (s <= 6 and m <= 8) else (16 if (s <= 14 and m <= 16) else (32 if s <= 24 else 256))
+
+
+def resolve_coupling(coupling, B, n, m):
+    coupling = coupling or DEFAULT_COUPLING
+    if coupling == "auto":
+        G = _group_size(n, m)
+        return "batch" if (G <= 32 and B * G <= 1024 and B * (n + m) ** 2 * 8 * 6 < 200 * 1024) else "element"
+    return coupling
+
+
+def scrambled_norm(du, B, T, m):
+    """reference :261-263: transpose(0,2,1).reshape(B, T*m) mixes batch elements (kept as is)."""
+    d = np.transpose(du, (0, 2, 1)).reshape(B, T * m)
+    return np.sqrt(np.sum(d ** 2, axis=1))
+
+
+class MPCstep(FunctionNodeBase):
+    def __init__(self, controls, T, u_upper, u_lower, n_batch, n_state, n_ctrl, current_states,
+                 true_cost, true_dynamics, ls_decay, max_ls_iter, verbose=False, need_expand=False,
+                 no_op_forward=False, coupling=None, device=0):
+        super().__init__()
+        self.controls = to_xp(controls)
+        self.u_upper = to_xp(u_upper)
+        self.u_lower = to_xp(u_lower)
+        self.n_state, self.n_ctrl, self.n_batch, self.T = int(n_state), int(n_ctrl), int(n_batch), int(T)
+        self.n_sc = self.n_state + self.n_ctrl
+        self.verbose = verbose
+        self.back_out = None
+        self.for_out = None
+        self.current_states = to_xp(current_states)
+        self.true_cost = true_cost
+        self.true_dynamics = true_dynamics
+        self.need_expand = need_expand
+        self.ls_decay = ls_decay
+        self.max_ls_iter = max_ls_iter
+        self.no_op_forward = no_op_forward
+        self.coupling = coupling
+        self._ctx = _native.default_context(device)
+        self._fwd = None       # retained host copies for backward
+        self.aux = None        # extra kernel outputs (Ks, ks, alphas, free masks, ...)
+
+    # ---- forward ---------------------------------------------------------------------------
+    def _forward_arrays(self, C_hat, c_hat, F_hat, f_hat):
+        T, B, n, m, s = self.T, self.n_batch, self.n_state, self.n_ctrl, self.n_sc
+        ctx = self._ctx
+        C_hat = as_f(C_hat)
+        dt = C_hat.dtype
+        c_hat, F_hat = as_f(c_hat, dt), as_f(F_hat, dt)
+        assert list(C_hat.shape) == [T, B, s, s], "C hat dim mismatch"
+        assert list(c_hat.shape) == [T, B, s], str(c_hat.shape) + " c hat dim mismatch: expected " + str([T, B, s])
+        assert F_hat.shape[0] in (T, T - 1), "F_hat dimension"
+        assert list(F_hat.shape[1:]) == [B, n, s], str(F_hat.shape) + "F_hat dim mismatch"
+        if f_hat is not None:
+            f_hat = as_f(f_hat, dt)
+            assert list(f_hat.shape) in ([T - 1, B, n], [T, B, n]), " f_hat dim mismatch"
+        u_nom, x_nom = as_f(self.controls, dt), as_f(self.current_states, dt)
+        lo, hi = as_f(self.u_lower, dt), as_f(self.u_upper, dt)
+        assert not np.isnan(u_nom).any() and not np.isnan(lo).any() and not np.isnan(hi).any()
+        assert (lo <= hi).all(), " lower is larger than upper"
+        if not isinstance(self.true_cost, QuadCost):
+            raise NotImplementedError("true_cost must be a util.QuadCost (callable costs cannot run in the fused kernel)")
+        tC, tc = as_f(self.true_cost.C, dt), as_f(self.true_cost.c, dt)
+        dC, dc, dF = ctx.to_device(C_hat), ctx.to_device(c_hat), ctx.to_device(F_hat)
+        df = None if (f_hat is None or self.need_expand) else ctx.to_device(f_hat[:T - 1])
+        dtC = dC if tC is C_hat or np.shares_memory(tC, C_hat) else ctx.to_device(tC)
+        dtc = dc if tc is c_hat or np.shares_memory(tc, c_hat) else ctx.to_device(tc)
+        if isinstance(self.true_dynamics, LinDx):
+            dyn, params = _native.DYN_LINEAR, None
+            tF = as_f(self.true_dynamics.F, dt)
+            tf = None if to_xp(self.true_dynamics.f) is None else as_f(self.true_dynamics.f, dt)
+            dtF = dF if np.shares_memory(tF, F_hat) else ctx.to_device(tF)
+            dtf = None if tf is None else ctx.to_device(tf)
+        elif is_pendulum(self.true_dynamics):
+            dyn, params = _native.DYN_PENDULUM, pendulum_params(self.true_dynamics)
+            dtF = dtf = None
+        else:
+            raise NotImplementedError("true_dynamics must be util.LinDx or a PendulumDx (SURVEY.md H3)")
+        coupling = resolve_coupling(self.coupling, B, n, m)
+        o = dict(x=ctx.empty((T, B, n), dt), u=ctx.empty((T, B, m), dt), Ks=ctx.empty((T, B, m, n), dt),
+                 ks=ctx.empty((T, B, m), dt), u_first=ctx.empty((T, B, m), dt), objs=ctx.empty((T, B), dt),
+                 costs=ctx.empty((B,), dt), old=ctx.empty((B,), dt), alphas=ctx.empty((B,), dt),
+                 n_qp=ctx.empty((T, B), np.int32), free=ctx.empty((T, B, m), np.uint8),
+                 n_ls=ctx.empty((B,), np.int32), flags=ctx.empty((B,), np.int32))
+        ctx.mpc_step_forward(dt, T, B, n, m, dC, dc, dF, F_hat.shape[0], df, ctx.to_device(x_nom), ctx.to_device(u_nom),
+                             ctx.to_device(lo), ctx.to_device(hi), dtC, dtc, dyn, dtF, dtf, params, self.ls_decay,
+                             MAX_LS_TRIALS, self.need_expand,
+                             _native.COUPLING_BATCH if coupling == "batch" else _native.COUPLING_ELEMENT,
+                             o["x"], o["u"], o["Ks"], o["ks"], o["u_first"], o["objs"], o["costs"], o["old"],
+                             o["alphas"], o["n_qp"], o["free"], o["n_ls"], o["flags"])
+        r = {k: v.download() for k, v in o.items()}
+        flags = r["flags"]
+        if (flags & _native.FLAG_QP_NOT_CONVERGED).any():
+            warnings.warn("Projected Newton Quadratic Programming warning: Did not converge")
+        if (flags & _native.FLAG_LS_CAPPED).any():
+            warnings.warn("MPCstep line search hit the %d-trial cap on %d elements" % (MAX_LS_TRIALS, int((flags & 4).astype(bool).sum())))
+        x, u = r["x"], r["u"]
+        assert not np.isnan(x).any() and not np.isnan(u).any()     # reference :284-285
+        self.back_out = LqrBackOut(n_total_qp_iter=int(r["n_qp"].max(axis=1).sum()))
+        self.for_out = LqrForOut(r["objs"], scrambled_norm(u_nom - r["u_first"], B, T, m),
+                                 scrambled_norm(u_nom - u, B, T, m), np.mean(r["alphas"]), r["costs"])
+        self.aux = dict(Ks=r["Ks"], ks=r["ks"], alphas=r["alphas"], free=r["free"], n_qp=r["n_qp"], n_ls=r["n_ls"],
+                        old_costs=r["old"], coupling=coupling, u_first=r["u_first"])
+        return x, u
+
+    def forward(self, inputs):
+        x_init, C_hat, c_hat, F_hat, f_hat = inputs
+        self.retain_inputs((0, 1, 2, 3, 4))
+        self._fwd = tuple(to_xp(v) for v in inputs)
+        if self.no_op_forward:
+            self.retain_outputs((0, 1))
+            self._out_xu = (np.asarray(self.current_states), np.asarray(self.controls))
+            return self.current_states, self.controls
+        x, u = self._forward_arrays(to_xp(C_hat), to_xp(c_hat), to_xp(F_hat), to_xp(f_hat))
+        self._out_xu = (x, u)
+        self.retain_outputs((0, 1))
+        return x, u
+
+    # ---- backward --------------------------------------------------------------------------
+    def backward_numpy(self, dl_dx, dl_du):
+        T, B, n, m, s = self.T, self.n_batch, self.n_state, self.n_ctrl, self.n_sc
+        ctx = self._ctx
+        x_init, C_hat, c_hat, F_hat, f_hat = self._fwd
+        C_hat = as_f(C_hat)
+        dt = C_hat.dtype
+        c_hat, F_hat = as_f(c_hat, dt), as_f(F_hat, dt)
+        new_x, new_u = as_f(self._out_xu[0], dt), as_f(self._out_xu[1], dt)
+        lo, hi = as_f(self.u_lower, dt), as_f(self.u_upper, dt)
+        gx = None if dl_dx is None else ctx.to_device(as_f(dl_dx, dt))
+        gu = None if dl_du is None else ctx.to_device(as_f(dl_du, dt))
+        if dl_dx is not None:
+            assert list(np.shape(dl_dx)) == [T, B, n]
+        if dl_du is not None:
+            assert list(np.shape(dl_du)) == [T, B, m]
+        FT = F_hat.shape[0]
+        wsK = ctx.empty((T, B, m, n), dt); wsk = ctx.empty((T, B, m), dt); wsd = ctx.empty((T, B, s), dt)
+        act = ctx.empty((T, B, m), np.uint8)
+        dx0 = ctx.empty((B, n), dt); dC = ctx.empty((T, B, s, s), dt); dc = ctx.empty((T, B, s), dt)
+        dF = ctx.empty((FT, B, n, s), dt)
+        df = ctx.empty((T - 1, B, n), dt) if (f_hat is not None and T > 1) else None
+        ctx.mpc_step_backward(dt, T, B, n, m, ctx.to_device(C_hat), ctx.to_device(c_hat), ctx.to_device(F_hat), FT,
+                              ctx.to_device(new_x), ctx.to_device(new_u), ctx.to_device(lo), ctx.to_device(hi), gx, gu,
+                              wsK, wsk, wsd, act, dx0, dC, dc, dF, df)
+        self.active_index = act.download().astype(bool)
+        return dx0.download(), dC.download(), dc.download(), dF.download(), (None if df is None else df.download())
+
+    def backward(self, target_input_indexes, grad_outputs):
+        dl_dx, dl_du = grad_outputs
+        g = self.backward_numpy(to_xp(dl_dx), to_xp(dl_du))
+        return tuple(wrap(v) for v in g)

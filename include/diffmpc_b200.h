@@ -123,6 +123,83 @@ int dmpc_lqr_adjoint(dmpc_handle h, int dtype, int T, int B, int n, int m,
                      void* d_dx0, void* d_dC, void* d_dc, void* d_dF, void* d_df,
                      int flags, void* stream);
 
+
+/* ---- PNQP (replaces PNQP, mpc/pnqp.py:37-201) ---------------------------------------------- */
+/*
+ * Batched projected-Newton box QP: min 0.5 x^T H x + q^T x  s.t. lower <= x <= upper.
+ *   d_H[B,m,m] d_q,d_lower,d_upper[B,m]; d_x_init[B,m] or NULL (pnqp.py:75-93).
+ * Outputs: d_x[B,m]; d_LU[B,m,m] + d_piv[B,m] (int32, 1-based LAPACK pivots) = factorisation of the
+ * last masked Hessian (+1e-11 I) (for m == 1, d_LU is the scalar H_f the reference returns);
+ * d_free[B,m] (1.0 = free, 0.0 = clamped, the reference's Index_f); d_iters[B] (int32, the
+ * reference's `i`; identical for all elements under DMPC_COUPLING_BATCH); d_flags[B] (nullable).
+ * lower <= upper is the caller's contract (the facade asserts it, pnqp.py:64).
+ */
+int dmpc_pnqp(dmpc_handle h, int dtype, int B, int m,
+              const void* d_H, const void* d_q, const void* d_lower, const void* d_upper, const void* d_x_init,
+              int n_iter, int coupling,
+              void* d_x, void* d_LU, void* d_piv, void* d_free, void* d_iters, void* d_flags, void* stream);
+
+/* ---- MPC step (replaces MPCstep, mpc/mpc_step.py:33-460) ------------------------------------ */
+/*
+ * MPCstep.forward (mpc_step.py:288-328): Taylor shift of c (need_expand), backward_rec with one
+ * PNQP per timestep (:70-173), forward_rec line search through the TRUE dynamics and cost (:175-286),
+ * fused in one launch.
+ *   model:      d_C[T,B,s,s] d_c[T,B,s] d_F[F_T,B,n,s] d_f[T-1,B,n] (NULL = None; ignored when need_expand)
+ *   nominal:    d_x_nom[T,B,n] (current_states)  d_u_nom[T,B,m] (controls)
+ *   bounds:     d_lower, d_upper [T,B,m]   (scalar bounds are broadcast by the caller, box_ddp.py:68-90)
+ *   true cost:  QuadCost d_tC[T,B,s,s], d_tc[T,B,s]  (may alias d_C, d_c)
+ *   true dyn:   DMPC_DYN_LINEAR with d_tF[>=T-1,B,n,s], d_tf (nullable)  or
+ *               DMPC_DYN_PENDULUM with h_dyn_params = {g, m, l} (env_dx/pendulum.py:31-102)
+ * Outputs: d_x[T,B,n] d_u[T,B,m]; gains d_Ks[T,B,m,n] d_ks[T,B,m]; d_u_first[T,B,m] = controls of the
+ * alpha=1 pass (for full_du_norm, :260-263); d_objs[T,B]; d_costs[B]; d_old_costs[B] (nullable);
+ * d_alphas[B]; d_n_qp[T,B] int32 (1 + PNQP iterations); d_free[T,B,m] uint8; d_n_ls[B] int32
+ * (line-search passes); d_flags[B] int32 (dmpc_elem_flag bits).
+ * max_ls_trials caps the per-element line search (the reference's loop has no effective cap, Q5).
+ */
+int dmpc_mpc_step_forward(dmpc_handle h, int dtype, int T, int B, int n, int m,
+                          const void* d_C, const void* d_c, const void* d_F, int F_T, const void* d_f,
+                          const void* d_x_nom, const void* d_u_nom, const void* d_lower, const void* d_upper,
+                          const void* d_tC, const void* d_tc, int dynamics, const void* d_tF, const void* d_tf,
+                          const double* h_dyn_params, double ls_decay, int max_ls_trials, int need_expand,
+                          int coupling,
+                          void* d_x, void* d_u, void* d_Ks, void* d_ks, void* d_u_first, void* d_objs,
+                          void* d_costs, void* d_old_costs, void* d_alphas, void* d_n_qp, void* d_free,
+                          void* d_n_ls, void* d_flags, void* stream);
+
+/*
+ * MPCstep.backward (mpc_step.py:330-460) incl. LQR_active (mpc/active_constrained_lqr.py:67-193).
+ *   d_x, d_u = the step's outputs (retained); d_gx[T,B,n], d_gu[T,B,m] = upstream grads (NULL = zeros).
+ * Workspaces (caller-owned): d_ws_Ks[T,B,m,n] d_ws_ks[T,B,m] d_ws_dtau[T,B,s] d_active[T,B,m] uint8
+ * (d_active doubles as an output: the active set used).
+ * Outputs: d_dx0[B,n] d_dC[T,B,s,s] d_dc[T,B,s] d_dF[F_T,B,n,s] (row T-1 zero-filled when F_T == T, Q8)
+ * d_df[T-1,B,n] (NULL when f_hat is None).
+ */
+int dmpc_mpc_step_backward(dmpc_handle h, int dtype, int T, int B, int n, int m,
+                           const void* d_C, const void* d_c, const void* d_F, int F_T,
+                           const void* d_x, const void* d_u, const void* d_lower, const void* d_upper,
+                           const void* d_gx, const void* d_gu,
+                           void* d_ws_Ks, void* d_ws_ks, void* d_ws_dtau, void* d_active,
+                           void* d_dx0, void* d_dC, void* d_dc, void* d_dF, void* d_df, void* stream);
+
+/*
+ * LQR_active.solve_recursion (mpc/active_constrained_lqr.py:195-202) on its own:
+ * d_active[T,B,m] uint8 = u_zero_Index.  Same tensors as dmpc_lqr_solve.
+ */
+int dmpc_lqr_active_solve(dmpc_handle h, int dtype, int T, int B, int n, int m,
+                          const void* d_x0, const void* d_C, const void* d_c, const void* d_F, int F_T,
+                          const void* d_f, const void* d_active,
+                          void* d_x, void* d_u, void* d_Ks, void* d_ks, void* stream);
+
+/* ---- trajectory helpers (util.get_traj util.py:201-236; PendulumDx env_dx/pendulum.py:65-102;
+ *      linearize_dynamics mpc/approximate.py:77-119 for the pendulum) -------------------------- */
+/*
+ * Roll x_{t+1} = dyn(x_t, u_t) from d_x0 under d_u[T,B,m] -> d_x[T,B,n].  For DMPC_DYN_PENDULUM
+ * (n=3, m=1) d_Fout[T-1,B,3,4] / d_fout[T-1,B,3] (nullable) receive the analytic linearisation.
+ */
+int dmpc_get_traj(dmpc_handle h, int dtype, int T, int B, int n, int m, int dynamics,
+                  const void* d_x0, const void* d_u, const void* d_F, const void* d_f,
+                  const double* h_dyn_params, void* d_x, void* d_Fout, void* d_fout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
