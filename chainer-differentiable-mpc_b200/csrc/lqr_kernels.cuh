@@ -54,13 +54,14 @@ struct LqrLayout {
   int Q, q, V, v, Mx, mv, H, Rhs, ldr, P, xcur, piv, total, stride;
 };
 
+// compact = rollout-only launch: the stage holds K_t (m*n) in the C slot and no Riccati work buffers
 template <typename R>
-__host__ __device__ inline LqrLayout lqr_layout(int n, int m, bool save_fac) {
+__host__ __device__ inline LqrLayout lqr_layout(int n, int m, bool save_fac, bool compact = false) {
   const int W = 16 / (int)sizeof(R);
   const int s = n + m;
   LqrLayout L;
   int o = 0;
-  L.oC = o; o += rup(s * s, W);
+  L.oC = o; o += rup(compact ? m * n : s * s, W);
   L.oc = o; o += rup(s, W);
   L.oF = o; o += rup(n * s, W);
   L.of_ = o; o += rup(n, W);
@@ -68,16 +69,20 @@ __host__ __device__ inline LqrLayout lqr_layout(int n, int m, bool save_fac) {
   o = 0;
   L.st0 = o; o += L.stage;
   L.st1 = o; o += L.stage;
-  L.Q = o; o += rup(s * s, W);
-  L.q = o; o += rup(s, W);
-  L.V = o; o += rup(n * n, W);
-  L.v = o; o += rup(n, W);
-  L.Mx = o; o += rup(n * s, W);
-  L.mv = o; o += rup(n, W);
-  L.H = o; o += rup(m * m, W);
   L.ldr = n + 1 + (save_fac ? m : 0);
-  L.Rhs = o; o += rup(m * L.ldr, W);
-  L.P = o; o += rup(m * (n + 1), W);
+  if (compact) {
+    L.Q = L.q = L.V = L.v = L.Mx = L.H = L.Rhs = L.P = 0;
+  } else {
+    L.Q = o; o += rup(s * s, W);
+    L.q = o; o += rup(s, W);
+    L.V = o; o += rup(n * n, W);
+    L.v = o; o += rup(n, W);
+    L.Mx = o; o += rup(n * s, W);
+    L.H = o; o += rup(m * m, W);
+    L.Rhs = o; o += rup(m * L.ldr, W);
+    L.P = o; o += rup(m * (n + 1), W);
+  }
+  L.mv = o; o += rup(n, W);
   L.xcur = o; o += rup(s, W);
   L.piv = o; o += rup((m * (int)sizeof(int) + (int)sizeof(R) - 1) / (int)sizeof(R), W);
   L.total = o;
@@ -103,7 +108,7 @@ __global__ void lqr_solve_kernel(LqrParams<R> p) {
   if (!valid) e = B - 1;
   const bool save_fac = (p.flags & LQR_SAVE_FAC) != 0;
   const bool masked = (p.flags & LQR_MASKED) != 0;
-  const LqrLayout L = lqr_layout<R>(n, m, save_fac);
+  const LqrLayout L = lqr_layout<R>(n, m, save_fac, !(p.flags & LQR_DO_FACTOR));
   R* sm = reinterpret_cast<R*>(smem_raw) + (size_t)eloc * L.stride;
   R* Q = sm + L.Q; R* q = sm + L.q; R* V = sm + L.V; R* v = sm + L.v;
   R* Mx = sm + L.Mx; R* mv = sm + L.mv; R* H = sm + L.H; R* Rhs = sm + L.Rhs; R* P = sm + L.P;

@@ -1,5 +1,8 @@
 // Kernel instantiation + shape dispatch for the LQR kernels (lqr_kernels.cuh).
+#include <cstdlib>
+#include <type_traits>
 #include "launch.h"
+#include "lqr_dmma.cuh"
 
 #ifndef DMPC_REAL
 #define DMPC_REAL double
@@ -39,10 +42,41 @@ static int do_launch(K kernel, const P& p, int G, size_t stride_bytes, int B, cu
   return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
 }
 
+static bool dmma_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DMPC_DISABLE_DMMA"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
+// n=32, m=8, fp64: Riccati sweep on DMMA (lqr_dmma.cuh) + a compact rollout launch
+static int launch_lqr_solve_dmma(const LqrParams<double>& p, cudaStream_t st, long long* nl) {
+  if (p.flags & LQR_DO_FACTOR) {
+    using Cfg = DmmaCfg<32, 8>;
+    const size_t smem = (size_t)Cfg::TOTAL * sizeof(double);
+    auto kern = lqr_factor_dmma_kernel<32, 8>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DMPC_ERR_CUDA;
+    kern<<<p.B, Cfg::NT, smem, st>>>(p);
+    if (nl) ++*nl;
+    if (cudaGetLastError() != cudaSuccess) return DMPC_ERR_CUDA;
+  }
+  if (p.flags & LQR_DO_ROLLOUT) {
+    LqrParams<double> q = p;
+    q.flags = LQR_DO_ROLLOUT;
+    const LqrLayout L = lqr_layout<double>(q.n, q.m, false, true);
+    return do_launch(lqr_solve_kernel<double, 32, 8, 32>, q, 32, (size_t)L.stride * sizeof(double), q.B, st, nl);
+  }
+  return DMPC_OK;
+}
+
 template <typename R>
 int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
   const ShapeInfo si = pick_shape_impl(p.n, p.m);
-  const LqrLayout L = lqr_layout<R>(p.n, p.m, (p.flags & LQR_SAVE_FAC) != 0);
+  if constexpr (std::is_same<R, double>::value) {
+    if (p.n == 32 && p.m == 8 && !(p.flags & LQR_MASKED) && p.c && p.c_scale == 1.0 && dmma_enabled())
+      return launch_lqr_solve_dmma(p, st, nl);
+  }
+  const bool compact = !(p.flags & LQR_DO_FACTOR);
+  const LqrLayout L = lqr_layout<R>(p.n, p.m, (p.flags & LQR_SAVE_FAC) != 0, compact);
   const size_t sb = (size_t)L.stride * sizeof(R);
 #define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) return do_launch(lqr_solve_kernel<R, N_, M_, G_>, p, G_, sb, p.B, st, nl);
   DMPC_SHAPES(X)
