@@ -26,61 +26,107 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = r * __fma_rn(-x, r, 2.0);
-  r = r * __fma_rn(-x, r, 2.0);
-  r = r * __fma_rn(-x, r, 2.0);
+  r = r * __fma_rn(-x, r, 2.0);      // 20 -> 40 bits
+  r = r * __fma_rn(-x, r, 2.0);      // 40 -> 80 bits
+  r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);   // final correction in residual form
   return r;
 }
 
 template <int N, int M>
 struct DmmaCfg {
-  static constexpr int S = N + M, NB = N / 8, SB = S / 8, NT = SB * 32;
-  static constexpr int LDV = N + 4, LDF = S + 4, LDK = N + 4;
+  static constexpr int S = N + M, NB = N / 8, SB = S / 8, NW = NB, NT = NW * 32;
+  static constexpr int LDV = N + 4, LDF = S + 4, LDK = N + 4, LDQI = M + 4;
   static constexpr int OC = 0, Oc = OC + S * LDF, OF = Oc + S, Of = OF + N * LDF, STG = Of + N;
-  static constexpr int OV = 2 * STG, Ov = OV + N * LDV, OMx = Ov + N, Omv = OMx + N * LDF, TOTAL = Omv + N;
+  static constexpr int OV = 2 * STG, Ov = OV + N * LDV, OMx = Ov + N, Omv = OMx + N * LDF, OQi = Omv + N,
+                       TOTAL = OQi + M * LDQI;
   static constexpr int OKk = OMx, OP = OMx + M * LDK;     // alias the dead Mx region after P2
-  static_assert(M == 8 && N % 8 == 0 && N >= 16, "DMMA path: m == 8, n multiple of 8");
+  static_assert(M == 8 && N == 32, "DMMA path is instantiated for n = 32, m = 8");
   static_assert(2 * M * LDK <= N * LDF, "Kk/P alias must fit in Mx");
-  static_assert(STG % 2 == 0 && OV % 2 == 0 && OMx % 2 == 0, "16B alignment");
+  static_assert(STG % 2 == 0 && OV % 2 == 0 && OMx % 2 == 0 && OQi % 2 == 0, "16B alignment");
 };
+
+__device__ __forceinline__ unsigned abs_hi(double x) { return (unsigned)__double2hiint(x) & 0x7fffffffu; }
+
+// Gauss-Jordan inverse of an 8 x 8 matrix by one warp: lane j < 8 holds column j of A, lane
+// 8 <= j < 16 holds column j-8 of I; after 8 pivot steps lanes 8..15 hold the columns of A^-1.
+// The pivot column is broadcast with shuffles; the (partial) pivot is chosen on the leading 32
+// bits of |a_ik| (ties within 2^-20 resolve to the first row - as stable as LAPACK's exact max).
+template <int M>
+__device__ __forceinline__ void warp_gj_inverse(double (&c)[M]) {
+  constexpr unsigned FULL = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < M; ++k) {
+    double pc[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) pc[i] = __shfl_sync(FULL, c[i], k);
+    int piv = k;
+    unsigned best = abs_hi(pc[k]);
+#pragma unroll
+    for (int i = k + 1; i < M; ++i) { const unsigned a = abs_hi(pc[i]); if (a > best) { best = a; piv = i; } }
+    if (piv != k) {                                  // warp-uniform
+#pragma unroll
+      for (int i = k + 1; i < M; ++i) {
+        if (piv == i) {
+          double tmp = c[i]; c[i] = c[k]; c[k] = tmp;
+          tmp = pc[i]; pc[i] = pc[k]; pc[k] = tmp;
+        }
+      }
+    }
+    const double rp = fast_rcp(pc[k]);
+    c[k] *= rp;
+#pragma unroll
+    for (int i = 0; i < M; ++i) if (i != k) c[i] = __fma_rn(-pc[i], c[k], c[i]);
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// warp-level 8x8 output tile: acc += A(8 x K) * B(K x 8), fragments fetched by the given functors
+#define DMPC_TILE_LOOP(acc0, acc1, K, AEXPR, BEXPR)            \
+  _Pragma("unroll") for (int k0 = 0; k0 < (K); k0 += 4) {      \
+    const double a_ = (AEXPR);                                 \
+    const double b_ = (BEXPR);                                 \
+    dmma884(acc0, acc1, a_, b_);                               \
+  }
 
 template <int N, int M>
 __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(LqrParams<double> p) {
   using Cfg = DmmaCfg<N, M>;
-  constexpr int S = Cfg::S, NB = Cfg::NB, SB = Cfg::SB, NT = Cfg::NT;
-  constexpr int LDV = Cfg::LDV, LDF = Cfg::LDF, LDK = Cfg::LDK;
+  constexpr int S = Cfg::S, NB = Cfg::NB, NT = Cfg::NT;
+  constexpr int LDV = Cfg::LDV, LDF = Cfg::LDF, LDK = Cfg::LDK, LDQI = Cfg::LDQI;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   double* V = sm + Cfg::OV; double* v = sm + Cfg::Ov; double* Mx = sm + Cfg::OMx; double* mv = sm + Cfg::Omv;
-  double* Kk = sm + Cfg::OKk; double* Pm = sm + Cfg::OP;
+  double* Kk = sm + Cfg::OKk; double* Pm = sm + Cfg::OP; double* Qi = sm + Cfg::OQi;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gr = lane >> 2, tg = lane & 3;
   const int T = p.T, B = p.B;
   const int e = blockIdx.x;
   const size_t tb = (size_t)B;
   const bool have_f = p.f != nullptr;
   const bool save_fac = (p.flags & LQR_SAVE_FAC) && p.fac;
+  // per-thread 16-byte chunk of a row: 20 chunks per row of S doubles, 6 rows in flight per pass
+  const int ld_cc = tid % (S / 2), ld_r0 = tid / (S / 2);
+  constexpr int LD_RSTEP = NT / (S / 2);          // 6 full rows per pass (threads >= 120 idle)
+  const bool ld_active = ld_r0 < LD_RSTEP;
 
   auto load_tiles = [&](int t, int st) {
     double* base = sm + st * Cfg::STG;
     const size_t idx = (size_t)t * tb + e;
-    const double* Cg = p.C + idx * S * S;
-    for (int c = tid; c < S * (S / 2); c += NT) {
-      const int row = c / (S / 2), cc = c - row * (S / 2);
-      cp_async16(base + Cfg::OC + row * LDF + cc * 2, Cg + row * S + cc * 2);
-    }
-    const double* cg = p.c + idx * S;
-    for (int c = tid; c < S / 2; c += NT) cp_async16(base + Cfg::Oc + c * 2, cg + c * 2);
-    if (t < T - 1) {
-      const double* Fg = p.F + idx * N * S;
-      for (int c = tid; c < N * (S / 2); c += NT) {
-        const int row = c / (S / 2), cc = c - row * (S / 2);
-        cp_async16(base + Cfg::OF + row * LDF + cc * 2, Fg + row * S + cc * 2);
-      }
-      if (have_f) {
-        const double* fg = p.f + idx * N;
-        for (int c = tid; c < N / 2; c += NT) cp_async16(base + Cfg::Of + c * 2, fg + c * 2);
+    if (ld_active) {
+      const double* Cg = p.C + idx * S * S + ld_cc * 2;
+      double* Cd = base + Cfg::OC + ld_cc * 2;
+      for (int r = ld_r0; r < S; r += LD_RSTEP) cp_async16(Cd + r * LDF, Cg + r * S);
+      if (t < T - 1) {
+        const double* Fg = p.F + idx * N * S + ld_cc * 2;
+        double* Fd = base + Cfg::OF + ld_cc * 2;
+        for (int r = ld_r0; r < N; r += LD_RSTEP) cp_async16(Fd + r * LDF, Fg + r * S);
       }
     }
+    if (tid < S / 2) cp_async16(base + Cfg::Oc + tid * 2, p.c + idx * S + tid * 2);
+    else if (t < T - 1 && have_f && tid >= 32 && tid < 32 + N / 2)
+      cp_async16(base + Cfg::Of + (tid - 32) * 2, p.f + idx * N + (tid - 32) * 2);
     cp_async_commit();
   };
 
@@ -88,63 +134,110 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
   int st = 0;
   for (int t = T - 1; t >= 0; --t) {
     if (t > 0) { load_tiles(t - 1, st ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
+    __syncthreads();                                                     // (0)
     double* base = sm + st * Cfg::STG;
     double* Q = base + Cfg::OC;        // C_t, overwritten in place by Q_t
     double* q = base + Cfg::Oc;        // c_t -> q_t
     const double* Ft = base + Cfg::OF;
     const double* ft = base + Cfg::Of;
+    const size_t idx = (size_t)t * tb + e;
     if (t < T - 1) {
-      // ---- P1: Mx = V F (warp = column block), mv = V f + v
+      // ---- phase A (all warps): VFu = V F[:, n:]  (row block = warp) ; mv = V f + v
+      {
+        double a0 = 0.0, a1 = 0.0;
+        DMPC_TILE_LOOP(a0, a1, N, V[(warp * 8 + gr) * LDV + k0 + tg], Ft[(k0 + tg) * LDF + N + gr])
+        *reinterpret_cast<double2*>(Mx + (warp * 8 + gr) * LDF + N + tg * 2) = make_double2(a0, a1);
+        const int i = tid >> 2, part = tid & 3;            // NT == 4 N
+        double sacc = 0.0;
+        if (have_f) {
+#pragma unroll
+          for (int k = 0; k < N / 4; ++k) sacc += V[i * LDV + part * (N / 4) + k] * ft[part * (N / 4) + k];
+        }
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        if (part == 0) mv[i] = sacc + v[i];
+      }
+      __syncthreads();                                                   // (1)
+    }
+    // ---- phase B: warp 0 -> Quu tile + Gauss-Jordan inverse ; warps 1..3 -> rest of Mx and Q
+    if (warp == 0) {
+      if (t < T - 1) {
+        const double2 c2 = *reinterpret_cast<const double2*>(Q + (N + gr) * LDF + N + tg * 2);
+        double a0 = c2.x, a1 = c2.y;
+        DMPC_TILE_LOOP(a0, a1, N, Ft[(k0 + tg) * LDF + N + gr], Mx[(k0 + tg) * LDF + N + gr])
+        *reinterpret_cast<double2*>(Q + (N + gr) * LDF + N + tg * 2) = make_double2(a0, a1);
+        __syncwarp();
+      }
+      double c[M];
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+        c[i] = (lane < M) ? Q[(N + i) * LDF + N + lane] : ((lane - M == i) ? 1.0 : 0.0);
+      warp_gj_inverse<M>(c);
+      if (lane >= M && lane < 2 * M) {
+        double* fg = save_fac ? p.fac + idx * (M * M + N * M) : nullptr;
+#pragma unroll
+        for (int i = 0; i < M; ++i) { Qi[i * LDQI + lane - M] = c[i]; if (fg) fg[i * M + lane - M] = c[i]; }
+      }
+    } else if (t < T - 1) {
+      const int w = warp - 1;                      // 0..2
+      // Mx[:, :n] = V F[:, :n] : row block `warp` (4 tiles) + a share of row block 0
       {
         double acc[NB][2];
 #pragma unroll
-        for (int ib = 0; ib < NB; ++ib) { acc[ib][0] = 0.0; acc[ib][1] = 0.0; }
+        for (int jb = 0; jb < NB; ++jb) { acc[jb][0] = 0.0; acc[jb][1] = 0.0; }
 #pragma unroll 2
         for (int k0 = 0; k0 < N; k0 += 4) {
-          const double b = Ft[(k0 + tg) * LDF + warp * 8 + gr];
+          const double a = V[(warp * 8 + gr) * LDV + k0 + tg];
 #pragma unroll
-          for (int ib = 0; ib < NB; ++ib) {
-            const double a = V[(ib * 8 + gr) * LDV + k0 + tg];
-            dmma884(acc[ib][0], acc[ib][1], a, b);
-          }
+          for (int jb = 0; jb < NB; ++jb) dmma884(acc[jb][0], acc[jb][1], a, Ft[(k0 + tg) * LDF + jb * 8 + gr]);
         }
 #pragma unroll
-        for (int ib = 0; ib < NB; ++ib)
-          *reinterpret_cast<double2*>(Mx + (ib * 8 + gr) * LDF + warp * 8 + tg * 2) = make_double2(acc[ib][0], acc[ib][1]);
-        if (tid < N * 4) {
-          const int i = tid >> 2, part = tid & 3;
-          double sacc = 0.0;
-          if (have_f) {
-#pragma unroll
-            for (int k = 0; k < N / 4; ++k) sacc += V[i * LDV + part * (N / 4) + k] * ft[part * (N / 4) + k];
-          }
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-          if (part == 0) mv[i] = sacc + v[i];
+        for (int jb = 0; jb < NB; ++jb)
+          *reinterpret_cast<double2*>(Mx + (warp * 8 + gr) * LDF + jb * 8 + tg * 2) = make_double2(acc[jb][0], acc[jb][1]);
+        // row block 0: warp 1 -> column blocks 0,1 ; warp 2 -> 2 ; warp 3 -> 3
+        const int jb0 = (w == 0) ? 0 : w + 1;
+        double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+#pragma unroll 2
+        for (int k0 = 0; k0 < N; k0 += 4) {
+          const double a = V[gr * LDV + k0 + tg];
+          dmma884(x0, x1, a, Ft[(k0 + tg) * LDF + jb0 * 8 + gr]);
+          if (w == 0) dmma884(y0, y1, a, Ft[(k0 + tg) * LDF + 8 + gr]);
         }
+        *reinterpret_cast<double2*>(Mx + gr * LDF + jb0 * 8 + tg * 2) = make_double2(x0, x1);
+        if (w == 0) *reinterpret_cast<double2*>(Mx + gr * LDF + 8 + tg * 2) = make_double2(y0, y1);
       }
-      __syncthreads();
-      // ---- P2: Q = C + F^T Mx (in place), q = c + F^T mv (in place)
+      named_bar_sync(1, NT - 32);                  // Mx complete among warps 1..3 (VFu came through (1))
+      // Q = C + F^T Mx except tile (u,u): row block `warp` (5 tiles) + 3 more tiles per warp
       {
-        double acc[SB][2];
+        double acc[NB + 1][2];
 #pragma unroll
-        for (int ib = 0; ib < SB; ++ib) {
-          const double2 c2 = *reinterpret_cast<const double2*>(Q + (ib * 8 + gr) * LDF + warp * 8 + tg * 2);
-          acc[ib][0] = c2.x; acc[ib][1] = c2.y;
+        for (int jb = 0; jb <= NB; ++jb) {
+          const double2 c2 = *reinterpret_cast<const double2*>(Q + (warp * 8 + gr) * LDF + jb * 8 + tg * 2);
+          acc[jb][0] = c2.x; acc[jb][1] = c2.y;
+        }
+        // extra tiles: id = 3 w + j over [(0,0) (0,1) (0,2) (0,3) (0,4) (4,0) (4,1) (4,2) (4,3)]
+        int xi[3], xj[3];
+        double ex[3][2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int id = 3 * w + j;
+          xi[j] = (id < 5) ? 0 : NB;
+          xj[j] = (id < 5) ? id : id - 5;
+          const double2 c2 = *reinterpret_cast<const double2*>(Q + (xi[j] * 8 + gr) * LDF + xj[j] * 8 + tg * 2);
+          ex[j][0] = c2.x; ex[j][1] = c2.y;
         }
 #pragma unroll 2
         for (int k0 = 0; k0 < N; k0 += 4) {
-          const double b = Mx[(k0 + tg) * LDF + warp * 8 + gr];
+          const double a = Ft[(k0 + tg) * LDF + warp * 8 + gr];
 #pragma unroll
-          for (int ib = 0; ib < SB; ++ib) {
-            const double a = Ft[(k0 + tg) * LDF + ib * 8 + gr];
-            dmma884(acc[ib][0], acc[ib][1], a, b);
-          }
+          for (int jb = 0; jb <= NB; ++jb) dmma884(acc[jb][0], acc[jb][1], a, Mx[(k0 + tg) * LDF + jb * 8 + gr]);
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            dmma884(ex[j][0], ex[j][1], Ft[(k0 + tg) * LDF + xi[j] * 8 + gr], Mx[(k0 + tg) * LDF + xj[j] * 8 + gr]);
         }
-        // q first (reads c), then the in-place stores of this warp's column block
-        if (tid < S * 4) {
-          const int i = tid >> 2, part = tid & 3;
+        // q = c + F^T mv (reads c in place) on the 96 threads of warps 1..3
+        for (int o = tid - 32; o < S * 4; o += NT - 32) {
+          const int i = o >> 2, part = o & 3;
           double sacc = 0.0;
 #pragma unroll
           for (int k = 0; k < N / 4; ++k) sacc += Ft[(part * (N / 4) + k) * LDF + i] * mv[part * (N / 4) + k];
@@ -152,151 +245,87 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
           sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
           if (part == 0) q[i] += sacc;
         }
+        // every Q tile is read and written by one warp only -> in-place stores need no barrier
 #pragma unroll
-        for (int ib = 0; ib < SB; ++ib)
-          *reinterpret_cast<double2*>(Q + (ib * 8 + gr) * LDF + warp * 8 + tg * 2) = make_double2(acc[ib][0], acc[ib][1]);
+        for (int jb = 0; jb <= NB; ++jb)
+          *reinterpret_cast<double2*>(Q + (warp * 8 + gr) * LDF + jb * 8 + tg * 2) = make_double2(acc[jb][0], acc[jb][1]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          *reinterpret_cast<double2*>(Q + (xi[j] * 8 + gr) * LDF + xj[j] * 8 + tg * 2) = make_double2(ex[j][0], ex[j][1]);
       }
-      __syncthreads();
     }
-    const size_t idx = (size_t)t * tb + e;
-    // ---- LU (warp 0): columns of [Quu | -Qux | -qu | I] live in registers, lane j <-> columns j and j+32
-    if (warp == 0) {
-      double ca[M], cb[M];
-      const int j2 = lane + 32;                 // second column index (valid if < NC)
-      constexpr int NC = M + N + 1 + M;
+    __syncthreads();                                                     // (2)
+    // ---- phase C (all warps): K = -Quu^-1 Qux (column block = warp), k = -Quu^-1 qu ; park Qxu
+    {
+      double a0 = 0.0, a1 = 0.0;
+      DMPC_TILE_LOOP(a0, a1, M, Qi[gr * LDQI + k0 + tg], Q[(N + k0 + tg) * LDF + warp * 8 + gr])
+      a0 = -a0; a1 = -a1;
+      *reinterpret_cast<double2*>(Kk + gr * LDK + warp * 8 + tg * 2) = make_double2(a0, a1);
+      *reinterpret_cast<double2*>(p.Ks + idx * M * N + gr * N + warp * 8 + tg * 2) = make_double2(a0, a1);
+      if (warp == 0 && lane < M) {
+        double kk = 0.0;
 #pragma unroll
-      for (int i = 0; i < M; ++i) {
-        if (lane < M) ca[i] = Q[(N + i) * LDF + N + lane];
-        else ca[i] = -Q[(N + i) * LDF + (lane - M)];
-        const int r = j2 - M;                   // rhs index of the second column
-        double vb = 0.0;
-        if (r < N) vb = -Q[(N + i) * LDF + r];
-        else if (r == N) vb = -q[N + i];
-        else if (r - N - 1 == i) vb = 1.0;
-        cb[i] = vb;
+        for (int l = 0; l < M; ++l) kk += Qi[lane * LDQI + l] * q[N + l];
+        Kk[lane * LDK + N] = -kk;
+        p.ks[idx * M + lane] = -kk;
       }
-#pragma unroll
-      for (int k = 0; k < M; ++k) {
-        double pc[M];
-#pragma unroll
-        for (int i = 0; i < M; ++i) pc[i] = __shfl_sync(0xffffffffu, ca[i], k);
-        int piv = k;
-        double best = fabs(pc[k]);
-#pragma unroll
-        for (int i = k + 1; i < M; ++i) { const double a = fabs(pc[i]); if (a > best) { best = a; piv = i; } }
-        double pv = pc[k];
-#pragma unroll
-        for (int i = k + 1; i < M; ++i) if (i == piv) pv = pc[i];
-        const double rp = fast_rcp(pv);
-        // row interchange k <-> piv on this lane's columns and on the broadcast pivot column
-#pragma unroll
-        for (int i = k + 1; i < M; ++i) {
-          if (i == piv) {
-            double tmp = ca[i]; ca[i] = ca[k]; ca[k] = tmp;
-            tmp = cb[i]; cb[i] = cb[k]; cb[k] = tmp;
-            pc[i] = pc[k];
-          }
-        }
-#pragma unroll
-        for (int i = k + 1; i < M; ++i) {
-          const double l = pc[i] * rp;
-          if (lane != k) ca[i] = __fma_rn(-l, ca[k], ca[i]); else ca[i] = l;
-          cb[i] = __fma_rn(-l, cb[k], cb[i]);
-        }
+      if (save_fac) {
+        double* fg = p.fac + idx * (M * M + N * M) + M * M;
+        for (int o = tid; o < N * M; o += NT) { const int i = o / M, j = o - i * M; fg[o] = Q[i * LDF + N + j]; }
       }
-      // back substitution: U(i,l) is row i of column l (lane l, l < M)
-#pragma unroll
-      for (int i = M - 1; i >= 0; --i) {
-        const double uii = __shfl_sync(0xffffffffu, ca[i], i);
-        const double ri = fast_rcp(uii);
-        double xa = ca[i], xb = cb[i];
-#pragma unroll
-        for (int l = i + 1; l < M; ++l) {
-          const double uil = __shfl_sync(0xffffffffu, ca[i], l);
-          xa = __fma_rn(-uil, ca[l], xa);
-          xb = __fma_rn(-uil, cb[l], xb);
-        }
-        if (lane >= M) ca[i] = xa * ri;
-        cb[i] = xb * ri;
-      }
-      // scatter: Kk (smem), K/k (global), Quu^-1 (global fac)
-      double* Kg = p.Ks + idx * M * N; double* kg = p.ks + idx * M;
-      double* fg = save_fac ? p.fac + idx * (M * M + N * M) : nullptr;
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-        if (lane >= M) { Kk[i * LDK + lane - M] = ca[i]; Kg[i * N + lane - M] = ca[i]; }
-        const int r = j2 - M;
-        if (r < N) { Kk[i * LDK + r] = cb[i]; Kg[i * N + r] = cb[i]; }
-        else if (r == N) { Kk[i * LDK + N] = cb[i]; kg[i] = cb[i]; }
-        else if (r < N + 1 + M && fg) fg[i * M + (r - N - 1)] = cb[i];
-      }
-      (void)NC;
-    } else if (save_fac) {
-      // the other warps park Qxu for the adjoint while warp 0 factorises
-      double* fg = p.fac + idx * (M * M + N * M) + M * M;
-      for (int o = tid - 32; o < N * M; o += NT - 32) { const int i = o / M, j = o - i * M; fg[o] = Q[i * LDF + N + j]; }
     }
-    __syncthreads();
+    __syncthreads();                                                     // (3)
     if (t > 0) {
-      // ---- P3: P = [Qux|qu] + Quu [K|k] ; V = Qxx + Qxu K + K^T P ; v = qx + Qxu k + K^T p
-      if (warp < NB) {
-        const int jb = warp;
-        {
-          const double2 c2 = *reinterpret_cast<const double2*>(Q + (N + gr) * LDF + jb * 8 + tg * 2);
-          double p0 = c2.x, p1 = c2.y;
+      // ---- phase D: P = [Qux|qu] + Quu [K|k] ; V = Qxx + Qxu K + K^T P ; v likewise (column block = warp)
+      const int jb = warp;
+      {
+        const double2 c2 = *reinterpret_cast<const double2*>(Q + (N + gr) * LDF + jb * 8 + tg * 2);
+        double p0 = c2.x, p1 = c2.y;
+        DMPC_TILE_LOOP(p0, p1, M, Q[(N + gr) * LDF + N + k0 + tg], Kk[(k0 + tg) * LDK + jb * 8 + gr])
+        *reinterpret_cast<double2*>(Pm + gr * LDK + jb * 8 + tg * 2) = make_double2(p0, p1);
+      }
+      __syncwarp();
+      double acc[NB][2];
 #pragma unroll
-          for (int k0 = 0; k0 < M; k0 += 4) {
-            const double a = Q[(N + gr) * LDF + N + k0 + tg];
-            const double b = Kk[(k0 + tg) * LDK + jb * 8 + gr];
-            dmma884(p0, p1, a, b);
-          }
-          *reinterpret_cast<double2*>(Pm + gr * LDK + jb * 8 + tg * 2) = make_double2(p0, p1);
-        }
-        __syncwarp();
-        double acc[NB][2];
+      for (int ib = 0; ib < NB; ++ib) {
+        const double2 c2 = *reinterpret_cast<const double2*>(Q + (ib * 8 + gr) * LDF + jb * 8 + tg * 2);
+        acc[ib][0] = c2.x; acc[ib][1] = c2.y;
+      }
+#pragma unroll
+      for (int k0 = 0; k0 < M; k0 += 4) {
+        const double b1 = Kk[(k0 + tg) * LDK + jb * 8 + gr];
+        const double b2 = Pm[(k0 + tg) * LDK + jb * 8 + gr];
 #pragma unroll
         for (int ib = 0; ib < NB; ++ib) {
-          const double2 c2 = *reinterpret_cast<const double2*>(Q + (ib * 8 + gr) * LDF + jb * 8 + tg * 2);
-          acc[ib][0] = c2.x; acc[ib][1] = c2.y;
-        }
-#pragma unroll
-        for (int k0 = 0; k0 < M; k0 += 4) {
-          const double b1 = Kk[(k0 + tg) * LDK + jb * 8 + gr];
-          const double b2 = Pm[(k0 + tg) * LDK + jb * 8 + gr];
-#pragma unroll
-          for (int ib = 0; ib < NB; ++ib) {
-            const double a1 = Q[(ib * 8 + gr) * LDF + N + k0 + tg];        // Qxu
-            dmma884(acc[ib][0], acc[ib][1], a1, b1);
-            const double a2 = Kk[(k0 + tg) * LDK + ib * 8 + gr];           // K^T
-            dmma884(acc[ib][0], acc[ib][1], a2, b2);
-          }
-        }
-#pragma unroll
-        for (int ib = 0; ib < NB; ++ib)
-          *reinterpret_cast<double2*>(V + (ib * 8 + gr) * LDV + jb * 8 + tg * 2) = make_double2(acc[ib][0], acc[ib][1]);
-      } else if (warp == NB) {
-        // vector part on the last warp: p = qu + Quu k ; v = qx + Qxu k + K^T p
-        double pj = 0.0;
-        if (lane < M) {
-          pj = q[N + lane];
-#pragma unroll
-          for (int l = 0; l < M; ++l) pj += Q[(N + lane) * LDF + N + l] * Kk[l * LDK + N];
-        }
-        double pb[M];
-#pragma unroll
-        for (int l = 0; l < M; ++l) pb[l] = __shfl_sync(0xffffffffu, pj, l);
-        for (int i = lane; i < N; i += 32) {
-          double a = q[i], b = 0.0;
-#pragma unroll
-          for (int l = 0; l < M; ++l) {
-            a += Q[i * LDF + N + l] * Kk[l * LDK + N];
-            b += Kk[l * LDK + i] * pb[l];
-          }
-          v[i] = a + b;
+          dmma884(acc[ib][0], acc[ib][1], Q[(ib * 8 + gr) * LDF + N + k0 + tg], b1);      // Qxu K
+          dmma884(acc[ib][0], acc[ib][1], Kk[(k0 + tg) * LDK + ib * 8 + gr], b2);         // K^T P
         }
       }
+#pragma unroll
+      for (int ib = 0; ib < NB; ++ib)
+        *reinterpret_cast<double2*>(V + (ib * 8 + gr) * LDV + jb * 8 + tg * 2) = make_double2(acc[ib][0], acc[ib][1]);
+      // vector part: p = qu + Quu k (lanes < M of every warp) ; v[8 warp + lane] = qx + Qxu k + K^T p
+      double pj = 0.0;
+      if (lane < M) {
+        pj = q[N + lane];
+#pragma unroll
+        for (int l = 0; l < M; ++l) pj += Q[(N + lane) * LDF + N + l] * Kk[l * LDK + N];
+      }
+      double pb[M];
+#pragma unroll
+      for (int l = 0; l < M; ++l) pb[l] = __shfl_sync(0xffffffffu, pj, l);
+      if (lane < 8) {
+        const int i = warp * 8 + lane;
+        double a = q[i], b = 0.0;
+#pragma unroll
+        for (int l = 0; l < M; ++l) {
+          a += Q[i * LDF + N + l] * Kk[l * LDK + N];
+          b += Kk[l * LDK + i] * pb[l];
+        }
+        v[i] = a + b;
+      }
     }
-    __syncthreads();
+    __syncthreads();                                                     // (4)
     st ^= 1;
   }
 }
