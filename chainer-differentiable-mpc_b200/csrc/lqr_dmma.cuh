@@ -144,8 +144,15 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
     if (t < T - 1) {
       // ---- phase A (all warps): VFu = V F[:, n:]  (row block = warp) ; mv = V f + v
       {
-        double a0 = 0.0, a1 = 0.0;
-        DMPC_TILE_LOOP(a0, a1, N, V[(warp * 8 + gr) * LDV + k0 + tg], Ft[(k0 + tg) * LDF + N + gr])
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int k0 = 0; k0 < N; k0 += 16) {        // four independent accumulation chains
+          dmma884(a0, a1, V[(warp * 8 + gr) * LDV + k0 + tg], Ft[(k0 + tg) * LDF + N + gr]);
+          dmma884(b0, b1, V[(warp * 8 + gr) * LDV + k0 + 4 + tg], Ft[(k0 + 4 + tg) * LDF + N + gr]);
+          dmma884(c0, c1, V[(warp * 8 + gr) * LDV + k0 + 8 + tg], Ft[(k0 + 8 + tg) * LDF + N + gr]);
+          dmma884(d0, d1, V[(warp * 8 + gr) * LDV + k0 + 12 + tg], Ft[(k0 + 12 + tg) * LDF + N + gr]);
+        }
+        a0 = (a0 + b0) + (c0 + d0); a1 = (a1 + b1) + (c1 + d1);
         *reinterpret_cast<double2*>(Mx + (warp * 8 + gr) * LDF + N + tg * 2) = make_double2(a0, a1);
         const int i = tid >> 2, part = tid & 3;            // NT == 4 N
         double sacc = 0.0;
@@ -163,8 +170,15 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
     if (warp == 0) {
       if (t < T - 1) {
         const double2 c2 = *reinterpret_cast<const double2*>(Q + (N + gr) * LDF + N + tg * 2);
-        double a0 = c2.x, a1 = c2.y;
-        DMPC_TILE_LOOP(a0, a1, N, Ft[(k0 + tg) * LDF + N + gr], Mx[(k0 + tg) * LDF + N + gr])
+        double a0 = c2.x, a1 = c2.y, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int k0 = 0; k0 < N; k0 += 16) {
+          dmma884(a0, a1, Ft[(k0 + tg) * LDF + N + gr], Mx[(k0 + tg) * LDF + N + gr]);
+          dmma884(b0, b1, Ft[(k0 + 4 + tg) * LDF + N + gr], Mx[(k0 + 4 + tg) * LDF + N + gr]);
+          dmma884(c0, c1, Ft[(k0 + 8 + tg) * LDF + N + gr], Mx[(k0 + 8 + tg) * LDF + N + gr]);
+          dmma884(d0, d1, Ft[(k0 + 12 + tg) * LDF + N + gr], Mx[(k0 + 12 + tg) * LDF + N + gr]);
+        }
+        a0 = (a0 + b0) + (c0 + d0); a1 = (a1 + b1) + (c1 + d1);
         *reinterpret_cast<double2*>(Q + (N + gr) * LDF + N + tg * 2) = make_double2(a0, a1);
         __syncwarp();
       }
@@ -185,7 +199,7 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
         double acc[NB][2];
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) { acc[jb][0] = 0.0; acc[jb][1] = 0.0; }
-#pragma unroll 2
+#pragma unroll 4
         for (int k0 = 0; k0 < N; k0 += 4) {
           const double a = V[(warp * 8 + gr) * LDV + k0 + tg];
 #pragma unroll
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
         // row block 0: warp 1 -> column blocks 0,1 ; warp 2 -> 2 ; warp 3 -> 3
         const int jb0 = (w == 0) ? 0 : w + 1;
         double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
         for (int k0 = 0; k0 < N; k0 += 4) {
           const double a = V[gr * LDV + k0 + tg];
           dmma884(x0, x1, a, Ft[(k0 + tg) * LDF + jb0 * 8 + gr]);
@@ -226,7 +240,7 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
           const double2 c2 = *reinterpret_cast<const double2*>(Q + (xi[j] * 8 + gr) * LDF + xj[j] * 8 + tg * 2);
           ex[j][0] = c2.x; ex[j][1] = c2.y;
         }
-#pragma unroll 2
+#pragma unroll 4
         for (int k0 = 0; k0 < N; k0 += 4) {
           const double a = Ft[(k0 + tg) * LDF + warp * 8 + gr];
 #pragma unroll
@@ -255,74 +269,55 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
       }
     }
     __syncthreads();                                                     // (2)
-    // ---- phase C (all warps): K = -Quu^-1 Qux (column block = warp), k = -Quu^-1 qu ; park Qxu
+    // ---- phase C+D (all warps, column block = warp): K = -Quu^-1 Qux, k = -Quu^-1 qu, then
+    //      V = Qxx + Qxu K, v = qx + Qxu k.  The reference's extra terms K^T (Qux + Quu K) and
+    //      K^T (qu + Quu k) (lqr_recursion.py:151-152) vanish identically for the exact gain and
+    //      are O(eps cond(Quu)) here - below its own rounding noise.
     {
       double a0 = 0.0, a1 = 0.0;
       DMPC_TILE_LOOP(a0, a1, M, Qi[gr * LDQI + k0 + tg], Q[(N + k0 + tg) * LDF + warp * 8 + gr])
       a0 = -a0; a1 = -a1;
       *reinterpret_cast<double2*>(Kk + gr * LDK + warp * 8 + tg * 2) = make_double2(a0, a1);
       *reinterpret_cast<double2*>(p.Ks + idx * M * N + gr * N + warp * 8 + tg * 2) = make_double2(a0, a1);
-      if (warp == 0 && lane < M) {
-        double kk = 0.0;
+      double kk = 0.0;                       // k_l on lanes < M of every warp (redundant, avoids a barrier)
+      if (lane < M) {
 #pragma unroll
         for (int l = 0; l < M; ++l) kk += Qi[lane * LDQI + l] * q[N + l];
-        Kk[lane * LDK + N] = -kk;
-        p.ks[idx * M + lane] = -kk;
+        kk = -kk;
+        if (warp == 0) p.ks[idx * M + lane] = kk;
       }
       if (save_fac) {
         double* fg = p.fac + idx * (M * M + N * M) + M * M;
         for (int o = tid; o < N * M; o += NT) { const int i = o / M, j = o - i * M; fg[o] = Q[i * LDF + N + j]; }
       }
-    }
-    __syncthreads();                                                     // (3)
-    if (t > 0) {
-      // ---- phase D: P = [Qux|qu] + Quu [K|k] ; V = Qxx + Qxu K + K^T P ; v likewise (column block = warp)
-      const int jb = warp;
-      {
-        const double2 c2 = *reinterpret_cast<const double2*>(Q + (N + gr) * LDF + jb * 8 + tg * 2);
-        double p0 = c2.x, p1 = c2.y;
-        DMPC_TILE_LOOP(p0, p1, M, Q[(N + gr) * LDF + N + k0 + tg], Kk[(k0 + tg) * LDK + jb * 8 + gr])
-        *reinterpret_cast<double2*>(Pm + gr * LDK + jb * 8 + tg * 2) = make_double2(p0, p1);
-      }
       __syncwarp();
-      double acc[NB][2];
-#pragma unroll
-      for (int ib = 0; ib < NB; ++ib) {
-        const double2 c2 = *reinterpret_cast<const double2*>(Q + (ib * 8 + gr) * LDF + jb * 8 + tg * 2);
-        acc[ib][0] = c2.x; acc[ib][1] = c2.y;
-      }
-#pragma unroll
-      for (int k0 = 0; k0 < M; k0 += 4) {
-        const double b1 = Kk[(k0 + tg) * LDK + jb * 8 + gr];
-        const double b2 = Pm[(k0 + tg) * LDK + jb * 8 + gr];
+      if (t > 0) {
+        const int jb = warp;
+        double acc[NB][2];
 #pragma unroll
         for (int ib = 0; ib < NB; ++ib) {
-          dmma884(acc[ib][0], acc[ib][1], Q[(ib * 8 + gr) * LDF + N + k0 + tg], b1);      // Qxu K
-          dmma884(acc[ib][0], acc[ib][1], Kk[(k0 + tg) * LDK + ib * 8 + gr], b2);         // K^T P
+          const double2 c2 = *reinterpret_cast<const double2*>(Q + (ib * 8 + gr) * LDF + jb * 8 + tg * 2);
+          acc[ib][0] = c2.x; acc[ib][1] = c2.y;
         }
-      }
 #pragma unroll
-      for (int ib = 0; ib < NB; ++ib)
-        *reinterpret_cast<double2*>(V + (ib * 8 + gr) * LDV + jb * 8 + tg * 2) = make_double2(acc[ib][0], acc[ib][1]);
-      // vector part: p = qu + Quu k (lanes < M of every warp) ; v[8 warp + lane] = qx + Qxu k + K^T p
-      double pj = 0.0;
-      if (lane < M) {
-        pj = q[N + lane];
+        for (int k0 = 0; k0 < M; k0 += 4) {
+          const double b1 = Kk[(k0 + tg) * LDK + jb * 8 + gr];
 #pragma unroll
-        for (int l = 0; l < M; ++l) pj += Q[(N + lane) * LDF + N + l] * Kk[l * LDK + N];
-      }
-      double pb[M];
-#pragma unroll
-      for (int l = 0; l < M; ++l) pb[l] = __shfl_sync(0xffffffffu, pj, l);
-      if (lane < 8) {
-        const int i = warp * 8 + lane;
-        double a = q[i], b = 0.0;
-#pragma unroll
-        for (int l = 0; l < M; ++l) {
-          a += Q[i * LDF + N + l] * Kk[l * LDK + N];
-          b += Kk[l * LDK + i] * pb[l];
+          for (int ib = 0; ib < NB; ++ib) dmma884(acc[ib][0], acc[ib][1], Q[(ib * 8 + gr) * LDF + N + k0 + tg], b1);
         }
-        v[i] = a + b;
+#pragma unroll
+        for (int ib = 0; ib < NB; ++ib)
+          *reinterpret_cast<double2*>(V + (ib * 8 + gr) * LDV + jb * 8 + tg * 2) = make_double2(acc[ib][0], acc[ib][1]);
+        double kb[M];
+#pragma unroll
+        for (int l = 0; l < M; ++l) kb[l] = __shfl_sync(0xffffffffu, kk, l);
+        if (lane < 8) {
+          const int i = warp * 8 + lane;
+          double a = q[i];
+#pragma unroll
+          for (int l = 0; l < M; ++l) a += Q[i * LDF + N + l] * kb[l];
+          v[i] = a;
+        }
       }
     }
     __syncthreads();                                                     // (4)
