@@ -24,7 +24,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "chainer-differentiable-mpc_b200")
-for p in (ROOT, PKG, os.path.join(PKG, "lqr"), os.path.join(PKG, "mpc")):
+for p in (ROOT, PKG, os.path.join(PKG, "lqr"), os.path.join(PKG, "mpc"), os.path.join(PKG, "env_dx")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -75,7 +75,7 @@ class ClockSampler:
                     self.rows.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def start(self):
         self._th = threading.Thread(target=self._run, daemon=True)
@@ -279,6 +279,11 @@ def run_b200(args):
             tcpu = min(cpu_lqr_fwd_bwd(n, m, T, Bc) for _ in range(2))
             line["cpu_baseline"] = {"value": Bc / tcpu, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "oracle port of DiffLqr.apply+backward, B_cpu=%d, same n/m/T, best of 2" % Bc}
+        if world == 1 and not args.no_latency:
+            try:
+                line["mpc_step_latency"] = mpc_step_latency(ctx, with_cpu=not args.no_cpu)
+            except Exception as ex:
+                line["mpc_step_latency"] = {"error": repr(ex)[:200]}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -333,16 +338,86 @@ def run_e2e(args, torch, ctx, n, m, T, world, dist, dev, rank):
             "batch_per_call": Be, "api": "DiffLqr.apply_numpy + backward_numpy (pinned host buffers)"}
 
 
+def mpc_step_latency(ctx, n_calls=200, cpu_calls=10, with_cpu=True):
+    """Second half of BASELINE's metric: batch-64 MPC-step p50 latency on the pendulum
+    (config 1: n=3, m=1, T=20, B=64, bounds +-2, as env_dx/il_exp.py wires it)."""
+    import _native
+    from mpc_step import MPCstep
+    from util import QuadCost
+    from pendulum_dx import PendulumDx
+    T, B, n, m = 20, 64, 3, 1
+    rs = np.random.RandomState(0)
+    th = rs.rand(B) * np.pi - np.pi / 2
+    x0 = np.stack((np.cos(th), np.sin(th), rs.rand(B) * 2 - 1), axis=1)
+    dx = PendulumDx()
+    qv, pv = dx.get_true_obj()
+    C = np.repeat(np.repeat(np.diag(qv)[None, None], T, 0), B, 1)
+    c = np.repeat(np.repeat(pv[None, None], T, 0), B, 1)
+    lo = np.full((T, B, m), -2.0); hi = np.full((T, B, m), 2.0)
+    u = np.zeros((T, B, m))
+    # nominal trajectory + linearisation on the device (as BoxDDP does each iteration)
+    xd = ctx.empty((T, B, n)); Fo = ctx.empty((T - 1, B, 3, 4)); fo = ctx.empty((T - 1, B, 3))
+    ctx.get_traj(np.float64, T, B, n, m, _native.DYN_PENDULUM, ctx.to_device(x0), ctx.to_device(u), None, None,
+                 (10.0, 1.0, 1.0), xd, Fo, fo)
+    x_nom, F, f = xd.download(), Fo.download(), fo.download()
+
+    def facade_call():
+        st = MPCstep(controls=u, T=T, u_upper=hi, u_lower=lo, n_batch=B, n_state=n, n_ctrl=m, current_states=x_nom,
+                     true_cost=QuadCost(C, c), true_dynamics=dx, ls_decay=0.2, max_ls_iter=5, need_expand=True)
+        return st.apply((x0, C, c, F, f))
+    for _ in range(10):
+        facade_call()
+    ts = []
+    for _ in range(n_calls):
+        t0 = time.perf_counter(); facade_call(); ts.append(time.perf_counter() - t0)
+    p50_facade = float(np.median(ts)) * 1e3
+    # device-resident: one C-ABI call + stream sync
+    d = {k: ctx.to_device(v) for k, v in dict(C=C, c=c, F=F, f=f, x=x_nom, u=u, lo=lo, hi=hi).items()}
+    o = dict(x=ctx.empty((T, B, n)), u=ctx.empty((T, B, m)), Ks=ctx.empty((T, B, m, n)), ks=ctx.empty((T, B, m)),
+             uf=ctx.empty((T, B, m)), objs=ctx.empty((T, B)), costs=ctx.empty((B,)), old=ctx.empty((B,)),
+             al=ctx.empty((B,)), nqp=ctx.empty((T, B), np.int32), fr=ctx.empty((T, B, m), np.uint8),
+             nls=ctx.empty((B,), np.int32), fl=ctx.empty((B,), np.int32))
+
+    def dev_call():
+        ctx.mpc_step_forward(np.float64, T, B, n, m, d["C"], d["c"], d["F"], T - 1, d["f"], d["x"], d["u"], d["lo"],
+                             d["hi"], d["C"], d["c"], _native.DYN_PENDULUM, None, None, (10.0, 1.0, 1.0), 0.2, 64, True,
+                             _native.COUPLING_BATCH, o["x"], o["u"], o["Ks"], o["ks"], o["uf"], o["objs"], o["costs"],
+                             o["old"], o["al"], o["nqp"], o["fr"], o["nls"], o["fl"])
+        ctx.sync()
+    for _ in range(10):
+        dev_call()
+    ts = []
+    for _ in range(n_calls):
+        t0 = time.perf_counter(); dev_call(); ts.append(time.perf_counter() - t0)
+    out = {"config": "c1 pendulum n=3 m=1 T=20 B=64 (one MPCstep.apply, need_expand, batch coupling)",
+           "p50_ms": p50_facade, "p50_ms_device_resident": float(np.median(ts)) * 1e3, "calls": n_calls,
+           "api": "MPCstep.apply with host numpy buffers (H2D+kernel+D2H) / dmpc_mpc_step_forward + sync"}
+    if with_cpu:
+        from oracle import mpc as ompc
+        import warnings
+        ts = []
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for _ in range(cpu_calls + 2):
+                t0 = time.perf_counter()
+                ompc.step_forward(C, c, F, f, x_nom, u, lo, hi, (C, c), ("pendulum", (10.0, 1.0, 1.0)), 0.2, 5, n, m,
+                                  need_expand=True, coupling="batch")
+                ts.append(time.perf_counter() - t0)
+        out["cpu_port_p50_ms"] = float(np.median(ts[2:])) * 1e3
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
     ap.add_argument("--e2e-batch", type=int, default=512)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -94,9 +94,7 @@ class DeviceArray:
         self.shape = tuple(int(v) for v in shape)
         self.dtype = np.dtype(dtype)
         self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
-        p = _vp()
-        ctx._check(ctx.lib.dmpc_malloc(ctx.h, self.nbytes, ctypes.byref(p)))
-        self.ptr = p.value
+        self.ptr = ctx._alloc(self.nbytes)
         self._owned = True
 
     def upload(self, arr, stream=None):
@@ -120,7 +118,7 @@ class DeviceArray:
 
     def free(self):
         if self._owned and self.ptr and self.ctx.h:
-            self.ctx.lib.dmpc_free(self.ctx.h, self.ptr)
+            self.ctx._release(self.ptr, self.nbytes)
         self.ptr = None
 
     def __del__(self):
@@ -150,6 +148,9 @@ class Context:
             raise DiffMpcError("dmpc_create(device=%d) failed: %s" % (device, self.lib.dmpc_status_string(rc).decode()))
         self.h = h
         self.device = int(device)
+        self._pool = {}          # nbytes -> [device pointers]; avoids cudaMalloc/cudaFree per call
+        self._pool_bytes = 0
+        self.pool_limit = 8 << 30
 
     def _check(self, rc):
         if rc != 0:
@@ -159,8 +160,37 @@ class Context:
                 raise AssertionError("%s: %s" % (msg, det))     # the reference raises AssertionError here
             raise DiffMpcError("%s: %s" % (msg, det))
 
+    def _alloc(self, nbytes):
+        lst = self._pool.get(nbytes)
+        if lst:
+            self._pool_bytes -= nbytes
+            return lst.pop()
+        p = _vp()
+        rc = self.lib.dmpc_malloc(self.h, nbytes, ctypes.byref(p))
+        if rc != 0 and self._pool:
+            self.trim()
+            rc = self.lib.dmpc_malloc(self.h, nbytes, ctypes.byref(p))
+        self._check(rc)
+        return p.value
+
+    def _release(self, ptr, nbytes):
+        if self._pool_bytes + nbytes > self.pool_limit:
+            self.lib.dmpc_free(self.h, ptr)
+            return
+        self._pool.setdefault(nbytes, []).append(ptr)
+        self._pool_bytes += nbytes
+
+    def trim(self):
+        """Return every cached buffer to the driver."""
+        for lst in self._pool.values():
+            for ptr in lst:
+                self.lib.dmpc_free(self.h, ptr)
+        self._pool.clear()
+        self._pool_bytes = 0
+
     def close(self):
         if self.h:
+            self.trim()
             self.lib.dmpc_destroy(self.h)
             self.h = None
 

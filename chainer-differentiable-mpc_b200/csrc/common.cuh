@@ -119,6 +119,24 @@ __device__ __forceinline__ void g_gemm(const Grp<G>& g, int I, int J, int K,
   }
 }
 
+// Row dot product sum_k row[k] * vec[k] started at element `rot` (wrapping): when lane o reads row o
+// of a row-major matrix, rot = o turns the access into a diagonal sweep that is shared-memory
+// bank-conflict free for any leading dimension; two interleaved accumulators shorten the chain.
+template <typename R>
+__device__ __forceinline__ R dot_rot(const R* row, const R* vec, int K, int rot, R init) {
+  R a0 = init, a1 = R(0);
+  int k = rot % K;
+  int i = 0;
+  for (; i + 1 < K; i += 2) {
+    int k1 = k + 1; if (k1 == K) k1 = 0;
+    a0 += row[k] * vec[k];
+    a1 += row[k1] * vec[k1];
+    k = k1 + 1; if (k == K) k = 0;
+  }
+  if (i < K) a0 += row[k] * vec[k];
+  return a0 + a1;
+}
+
 // In-place LU with partial pivoting of H[m x m] (row-major, ld = ldh) carrying `ncols`
 // right-hand-side columns of Rhs[m x ncols] (ld = ldr) through the same row operations
 // (i.e. afterwards Rhs = L^-1 P Rhs).  piv (1-based, LAPACK convention) may be nullptr.

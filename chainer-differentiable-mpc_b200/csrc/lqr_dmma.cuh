@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
         double sacc = 0.0;
         if (have_f) {
 #pragma unroll
-          for (int k = 0; k < N / 4; ++k) sacc += V[i * LDV + part * (N / 4) + k] * ft[part * (N / 4) + k];
+          for (int k = 0; k < N / 4; ++k) sacc += V[i * LDV + 4 * k + part] * ft[4 * k + part];   // interleaved split: bank-conflict free
         }
         sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
         sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
           const int i = o >> 2, part = o & 3;
           double sacc = 0.0;
 #pragma unroll
-          for (int k = 0; k < N / 4; ++k) sacc += Ft[(part * (N / 4) + k) * LDF + i] * mv[part * (N / 4) + k];
+          for (int k = 0; k < N / 4; ++k) sacc += Ft[(4 * k + part) * LDF + i] * mv[4 * k + part];
           sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
           sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
           if (part == 0) q[i] += sacc;

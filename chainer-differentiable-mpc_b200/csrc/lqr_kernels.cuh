@@ -252,11 +252,7 @@ __global__ void lqr_solve_kernel(LqrParams<R> p) {
       const R* Kt = base + L.oC; const R* kt = base + L.oc; const R* Ft = base + L.oF; const R* ft = base + L.of_;
       const unsigned char* act = masked ? (p.active + ((size_t)t * tb + e) * m) : nullptr;
       for (int o = g.lane; o < m; o += G) {
-        R a0 = kt[o], a1 = R(0);
-        int k = 0;
-        for (; k + 1 < n; k += 2) { a0 += Kt[o * n + k] * xcur[k]; a1 += Kt[o * n + k + 1] * xcur[k + 1]; }
-        if (k < n) a0 += Kt[o * n + k] * xcur[k];
-        R uv = a0 + a1;
+        R uv = dot_rot(Kt + o * n, xcur, n, o, kt[o]);
         if (masked && act[o]) uv = R(0);      // active_constrained_lqr.py:175
         xcur[n + o] = uv;
       }
@@ -271,13 +267,7 @@ __global__ void lqr_solve_kernel(LqrParams<R> p) {
       }
       if (t < T - 1) {
         // x' = F [x;u] + f  -> into mv then copy
-        for (int o = g.lane; o < n; o += G) {
-          R a0 = p.f ? ft[o] : R(0), a1 = R(0);
-          int k = 0;
-          for (; k + 1 < s; k += 2) { a0 += Ft[o * s + k] * xcur[k]; a1 += Ft[o * s + k + 1] * xcur[k + 1]; }
-          if (k < s) a0 += Ft[o * s + k] * xcur[k];
-          mv[o] = a0 + a1;
-        }
+        for (int o = g.lane; o < n; o += G) mv[o] = dot_rot(Ft + o * s, xcur, s, o, p.f ? ft[o] : R(0));
         g.sync();
         for (int o = g.lane; o < n; o += G) xcur[o] = mv[o];
       }
@@ -380,15 +370,11 @@ __global__ void lqr_dtau_kernel(DtauParams<R> p) {
       }
       g.sync();
       for (int o = g.lane; o < m; o += G) {
-        R a = R(0);
-        for (int l = 0; l < m; ++l) a += Qi[o * m + l] * q[n + l];
-        kp[o] = -a;
+        kp[o] = -dot_rot(Qi + o * m, q + n, m, o, R(0));
       }
       g.sync();
       for (int o = g.lane; o < n; o += G) {
-        R a = q[o];
-        for (int l = 0; l < m; ++l) a += Qxu[o * m + l] * kp[l];
-        vp[o] = a;
+        vp[o] = dot_rot(Qxu + o * m, kp, m, o, q[o]);
       }
       if (valid) for (int o = g.lane; o < m; o += G) p.dc[((size_t)t * tb + e) * s + n + o] = kp[o];
       g.sync();
@@ -414,23 +400,11 @@ __global__ void lqr_dtau_kernel(DtauParams<R> p) {
       g.sync();
       const R* base = sm + (st ? L.st1 : L.st0);
       const R* Ft = base + L.oF; const R* Kt = base + L.oA; const R* kpt = base + L.og;
-      for (int o = g.lane; o < m; o += G) {
-        R a0 = kpt[o], a1 = R(0);
-        int k = 0;
-        for (; k + 1 < n; k += 2) { a0 += Kt[o * n + k] * dx[k]; a1 += Kt[o * n + k + 1] * dx[k + 1]; }
-        if (k < n) a0 += Kt[o * n + k] * dx[k];
-        dx[n + o] = a0 + a1;
-      }
+      for (int o = g.lane; o < m; o += G) dx[n + o] = dot_rot(Kt + o * n, dx, n, o, kpt[o]);
       g.sync();
       if (valid) for (int o = g.lane; o < s; o += G) p.dc[((size_t)t * tb + e) * s + o] = dx[o];
       if (t < T - 1) {
-        for (int o = g.lane; o < n; o += G) {
-          R a0 = R(0), a1 = R(0);
-          int k = 0;
-          for (; k + 1 < s; k += 2) { a0 += Ft[o * s + k] * dx[k]; a1 += Ft[o * s + k + 1] * dx[k + 1]; }
-          if (k < s) a0 += Ft[o * s + k] * dx[k];
-          tmp[o] = a0 + a1;
-        }
+        for (int o = g.lane; o < n; o += G) tmp[o] = dot_rot(Ft + o * s, dx, s, o, R(0));
         g.sync();
         for (int o = g.lane; o < n; o += G) dx[o] = tmp[o];
       }
@@ -543,8 +517,8 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
       R a0, a1 = R(0);
       if (isd) a0 = p.gx ? rsgn * gxt[i] : R(0); else a0 = ct[i];
       const R* ln = isd ? dlam : lam;
-      if (isd) { for (int j = 0; j < s; ++j) a0 += Ct[i * s + j] * dt[j]; }
-      else     { for (int j = 0; j < s; ++j) a0 += Ct[i * s + j] * tau(j); }
+      if (isd) { a0 = dot_rot(Ct + i * s, dt, s, i, a0); }
+      else     { int j = i % s; for (int c = 0; c < s; ++c) { a0 += Ct[i * s + j] * tau(j); if (++j == s) j = 0; } }
       if (t < T - 1) for (int k = 0; k < n; ++k) a1 += Ft[k * s + i] * ln[k];
       (isd ? dlamn : lamn)[i] = a0 + a1;
     }
