@@ -178,32 +178,54 @@ def run_b200(args):
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
     ctx = _native.Context(local)
-    pr = make_problem_torch(torch, dev, n, m, T, B, seed=1234 + rank)
     f64 = torch.float64
-    out = dict(x=torch.empty(T, B, n, dtype=f64, device=dev), u=torch.empty(T, B, m, dtype=f64, device=dev),
-               Ks=torch.empty(T, B, m, n, dtype=f64, device=dev), ks=torch.empty(T, B, m, dtype=f64, device=dev),
-               fac=torch.empty(T, B, m * m + n * m, dtype=f64, device=dev),
-               dx0=torch.empty(B, n, dtype=f64, device=dev), dC=torch.empty(T, B, s, s, dtype=f64, device=dev),
-               dc=torch.empty(T, B, s, dtype=f64, device=dev), dF=torch.empty(T - 1, B, n, s, dtype=f64, device=dev),
-               df=torch.empty(T - 1, B, n, dtype=f64, device=dev))
-    # a non-default torch stream: its handle is passed to the C ABI (NULL would mean the
-    # library's own stream) and the CUDA events below are recorded on the same stream
-    tstream = torch.cuda.Stream(device=dev)
+    K = max(1, args.chunks)
+    assert B % K == 0, "--chunks must divide the per-GPU batch"
+    Bc = B // K
+    # K independent sub-batches (contiguous [T,Bc,...] tensors each): fwd(i+1) overlaps bwd(i) on two streams
+    chunks = []
+    for i in range(K):
+        pr = make_problem_torch(torch, dev, n, m, T, Bc, seed=1234 + 1000 * rank + i)
+        out = dict(x=torch.empty(T, Bc, n, dtype=f64, device=dev), u=torch.empty(T, Bc, m, dtype=f64, device=dev),
+                   Ks=torch.empty(T, Bc, m, n, dtype=f64, device=dev), ks=torch.empty(T, Bc, m, dtype=f64, device=dev),
+                   fac=torch.empty(T, Bc, m * m + n * m, dtype=f64, device=dev),
+                   dx0=torch.empty(Bc, n, dtype=f64, device=dev), dC=torch.empty(T, Bc, s, s, dtype=f64, device=dev),
+                   dc=torch.empty(T, Bc, s, dtype=f64, device=dev), dF=torch.empty(T - 1, Bc, n, s, dtype=f64, device=dev),
+                   df=torch.empty(T - 1, Bc, n, dtype=f64, device=dev))
+        chunks.append((pr, out))
+    # non-default torch streams: their handles are passed to the C ABI (NULL would mean the library's own
+    # stream) and the CUDA events below are recorded on the same streams
+    sA = torch.cuda.Stream(device=dev)
+    sB = torch.cuda.Stream(device=dev, priority=-1) if K > 1 else sA
     torch.cuda.synchronize()
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-    assert stream != 0
     P = lambda t: t.data_ptr()
 
-    def fwd():
-        ctx.lqr_solve(np.float64, T, B, n, m, P(pr["x0"]), P(pr["C"]), P(pr["c"]), P(pr["F"]), T - 1, P(pr["f"]),
-                      P(out["x"]), P(out["u"]), P(out["Ks"]), P(out["ks"]), P(out["fac"]),
-                      _native.LQR_FACTOR | _native.LQR_ROLLOUT | _native.LQR_SAVE_FAC, stream)
+    def fwd(i, stream, flags):
+        pr, out = chunks[i]
+        ctx.lqr_solve(np.float64, T, Bc, n, m, P(pr["x0"]), P(pr["C"]), P(pr["c"]), P(pr["F"]), T - 1, P(pr["f"]),
+                      P(out["x"]), P(out["u"]), P(out["Ks"]), P(out["ks"]), P(out["fac"]), flags, stream.cuda_stream)
 
-    def bwd():
-        ctx.lqr_adjoint(np.float64, T, B, n, m, P(pr["C"]), P(pr["c"]), P(pr["F"]), P(out["x"]), P(out["u"]),
+    def bwd(i, stream):
+        pr, out = chunks[i]
+        ctx.lqr_adjoint(np.float64, T, Bc, n, m, P(pr["C"]), P(pr["c"]), P(pr["F"]), P(out["x"]), P(out["u"]),
                         P(pr["gx"]), P(pr["gu"]), P(out["Ks"]), P(out["fac"]), P(out["dx0"]), P(out["dC"]),
-                        P(out["dc"]), P(out["dF"]), P(out["df"]), _native.ADJ_STRICT_REFERENCE, stream)
+                        P(out["dc"]), P(out["dF"]), P(out["df"]), _native.ADJ_STRICT_REFERENCE, stream.cuda_stream)
+
+    FULL = _native.LQR_FACTOR | _native.LQR_ROLLOUT | _native.LQR_SAVE_FAC
+
+    def step():
+        """fwd+bwd of the whole per-GPU batch; backward of chunk i waits for forward of chunk i."""
+        for i in range(K):
+            fwd(i, sA, FULL)
+            if K > 1:
+                ev = torch.cuda.Event()
+                ev.record(sA)
+                sB.wait_event(ev)
+            bwd(i, sB)
+        if K > 1:
+            ev = torch.cuda.Event()
+            ev.record(sB)
+            sA.wait_event(ev)
 
     def barrier():
         if dist is not None:
@@ -211,59 +233,73 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        fwd(); bwd()
+        step()
     barrier()
-    # per-kernel timing of the dominant kernels (events on the launching stream)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    # ---- kernel-level durations (serial, chunk 0, events on the launching stream) for the roofline
+    kt = {"factor": [], "rollout": [], "adjoint": []}
+    for _ in range(3):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(sA)
+        fwd(0, sA, _native.LQR_FACTOR | _native.LQR_SAVE_FAC); e[1].record(sA)
+        fwd(0, sA, _native.LQR_ROLLOUT); e[2].record(sA)
+        bwd(0, sA); e[3].record(sA)
+        torch.cuda.synchronize()
+        kt["factor"].append(e[0].elapsed_time(e[1])); kt["rollout"].append(e[1].elapsed_time(e[2]))
+        kt["adjoint"].append(e[2].elapsed_time(e[3]))
+    kt = {k: float(np.mean(v)) for k, v in kt.items()}
+    # ---- timed region
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ctx.launches
     barrier()
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    k = 0
-    ev[0].record()
+    t_start.record(sA)
     for _ in range(args.steps):
-        fwd(); ev[k + 1].record()
-        bwd(); ev[k + 2].record()
-        k += 2
-    t_end.record()
+        step()
+    t_end.record(sA)
     barrier()
     launches = ctx.launches - l0
     clocks = sampler.stop()
     ms_total = t_start.elapsed_time(t_end)
-    fwd_ms = np.mean([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)])
-    bwd_ms = np.mean([ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)])
     if dist is not None:
         tt = torch.tensor([ms_total], dtype=f64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
-
-    # sanity: finite outputs (a fast wrong kernel is not done)
-    ok = bool(torch.isfinite(out["x"]).all().item() and torch.isfinite(out["dF"]).all().item())
+    ok = all(bool(torch.isfinite(o["x"]).all().item() and torch.isfinite(o["dF"]).all().item()) for _, o in chunks)
 
     line = None
     if rank == 0:
         fwd_b, tot_b = algorithmic_bytes(n, m, T)
         peak, peak_src = measured_peaks()
-        # dominant kernel = lqr_solve_kernel (forward): algorithmic fwd bytes / its launch duration
-        dom_ms, dom_bytes, dom_name = (fwd_ms, fwd_b, "lqr_solve_kernel") if fwd_ms >= bwd_ms else (bwd_ms, tot_b - fwd_b, "lqr_dtau_kernel+adjoint_out_kernel")
-        achieved = B * dom_bytes / (dom_ms * 1e-3) / 1e9
+        # dominant kernel = the Riccati sweep; its algorithmic bytes are the forward reads (C,c,F,f,x0)
+        fac_b = fwd_b - 8 * T * s
+        dom = max(kt, key=kt.get)
+        dom_bytes = {"factor": fac_b, "rollout": 8 * ((T - 1) * (n * s + n) + T * (m * n + m) + T * s + n),
+                     "adjoint": tot_b - fwd_b}[dom]
+        dom_name = {"factor": "lqr_factor_dmma_kernel" if (n, m) == (32, 8) else "lqr_solve_kernel(FACTOR)",
+                    "rollout": "lqr_solve_kernel(ROLLOUT)", "adjoint": "lqr_dtau_kernel+adjoint_out_kernel"}[dom]
+        achieved = Bc * dom_bytes / (kt[dom] * 1e-3) / 1e9
         whole = B * tot_b / (ms_step * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms_per_chunk": kt, "chunk_batch": Bc,
+                "whole_step_achieved": whole, "whole_step_frac": whole / peak,
+                "algorithmic_bytes_per_solve": {"fwd": fwd_b, "fwd_bwd": tot_b}}
+        if (n, m) == (32, 8):
+            flops = 400 * 512 * T          # DMMA flops of the Riccati sweep per solve
+            tf = Bc * flops / (kt["factor"] * 1e-3) / 1e12
+            roof["fp64_tensor"] = {"achieved_tflops": tf, "peak_tflops": 37.15, "frac": tf / 37.15,
+                                   "peak_source": "measured, profiles/r1/fp64_peak.json"}
         line = {"metric": "lqr_fwd_bwd_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "desc": desc, "n_state": n, "n_ctrl": m, "T": T,
                            "batch_per_gpu": B, "global_batch": B * world, "parallelism": "batch-sharded x%d" % world,
+                           "chunks_per_gpu": K, "overlap": "fwd(chunk i+1) || bwd(chunk i) on two streams" if K > 1 else "none",
                            "l2": "inputs (%.1f GB/GPU) larger than L2" % (B * fwd_b / 1e9), "finite_outputs": ok},
-                "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
-                             "whole_step_achieved": whole, "whole_step_frac": whole / peak,
-                             "algorithmic_bytes_per_solve": {"fwd": fwd_b, "fwd_bwd": tot_b}},
-                "clocks": clocks, "gpu_launches": launches}
+                "roofline": roof, "clocks": clocks, "gpu_launches": launches}
 
     # ---- e2e through the public API with host buffers (rank-local chunk) -----------------
     e2e = None
@@ -274,16 +310,20 @@ def run_b200(args):
     if rank == 0:
         line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
-            Bc = cpu_sample_batch(n, m, T)
-            cpu_lqr_fwd_bwd(n, m, T, min(Bc, 32))
-            tcpu = min(cpu_lqr_fwd_bwd(n, m, T, Bc) for _ in range(2))
-            line["cpu_baseline"] = {"value": Bc / tcpu, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "oracle port of DiffLqr.apply+backward, B_cpu=%d, same n/m/T, best of 2" % Bc}
+            Bcpu = cpu_sample_batch(n, m, T)
+            cpu_lqr_fwd_bwd(n, m, T, min(Bcpu, 32))
+            tcpu = min(cpu_lqr_fwd_bwd(n, m, T, Bcpu) for _ in range(2))
+            line["cpu_baseline"] = {"value": Bcpu / tcpu, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "oracle port of DiffLqr.apply+backward, B_cpu=%d, same n/m/T, best of 2" % Bcpu}
         if world == 1 and not args.no_latency:
             try:
                 line["mpc_step_latency"] = mpc_step_latency(ctx, with_cpu=not args.no_cpu)
             except Exception as ex:
                 line["mpc_step_latency"] = {"error": repr(ex)[:200]}
+            try:
+                line["mpc_step_throughput"] = mpc_step_throughput(ctx, torch, dev)
+            except Exception as ex:
+                line["mpc_step_throughput"] = {"error": repr(ex)[:200]}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -407,6 +447,55 @@ def mpc_step_latency(ctx, n_calls=200, cpu_calls=10, with_cpu=True):
     return out
 
 
+def mpc_step_throughput(ctx, torch, dev, B=16384, reps=5):
+    """BASELINE config 3: box-constrained MPC step sweep n=8, m=4, T=50, B=16384, bounds tuned so that
+    roughly 30 % of the timesteps have a clamped control; device-resident, element coupling."""
+    import _native
+    T, n, m = 50, 8, 4
+    s = n + m
+    pr = make_problem_torch(torch, dev, n, m, T, B, seed=77)
+    f64 = torch.float64
+    bound = 0.6
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    u = torch.clamp(0.2 * torch.randn(T, B, m, dtype=f64, device=dev, generator=g), -bound, bound)
+    lo = torch.full((T, B, m), -bound, dtype=f64, device=dev); hi = -lo
+    x = torch.empty(T, B, n, dtype=f64, device=dev)
+    P = lambda t: t.data_ptr()
+    st = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    sh = st.cuda_stream
+    ctx.get_traj(np.float64, T, B, n, m, _native.DYN_LINEAR, P(pr["x0"]), P(u), P(pr["F"]), P(pr["f"]), None, P(x), None, None, sh)
+    o = dict(x=torch.empty_like(x), u=torch.empty_like(u), Ks=torch.empty(T, B, m, n, dtype=f64, device=dev),
+             ks=torch.empty(T, B, m, dtype=f64, device=dev), uf=torch.empty_like(u), objs=torch.empty(T, B, dtype=f64, device=dev),
+             costs=torch.empty(B, dtype=f64, device=dev), old=torch.empty(B, dtype=f64, device=dev),
+             al=torch.empty(B, dtype=f64, device=dev), nqp=torch.empty(T, B, dtype=torch.int32, device=dev),
+             fr=torch.empty(T, B, m, dtype=torch.uint8, device=dev), nls=torch.empty(B, dtype=torch.int32, device=dev),
+             fl=torch.empty(B, dtype=torch.int32, device=dev))
+
+    def call():
+        ctx.mpc_step_forward(np.float64, T, B, n, m, P(pr["C"]), P(pr["c"]), P(pr["F"]), T - 1, P(pr["f"]), P(x), P(u),
+                             P(lo), P(hi), P(pr["C"]), P(pr["c"]), _native.DYN_LINEAR, P(pr["F"]), P(pr["f"]), None, 0.2, 64,
+                             True, _native.COUPLING_ELEMENT, P(o["x"]), P(o["u"]), P(o["Ks"]), P(o["ks"]), P(o["uf"]),
+                             P(o["objs"]), P(o["costs"]), P(o["old"]), P(o["al"]), P(o["nqp"]), P(o["fr"]), P(o["nls"]),
+                             P(o["fl"]), sh)
+    for _ in range(2):
+        call()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps):
+        call()
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    clamped_steps = float(((o["u"] <= -bound + 1e-8) | (o["u"] >= bound - 1e-8)).any(dim=2).double().mean().item())
+    return {"config": "c3 n=8 m=4 T=50 B=%d box-constrained MPC step (element coupling), bounds +-%.1f" % (B, bound),
+            "ms_per_step": ms, "mpc_steps_per_sec": B / (ms * 1e-3), "clamped_timestep_frac": clamped_steps,
+            "mean_qp_iters_per_timestep": float(o["nqp"].double().mean().item()),
+            "mean_line_search_passes": float(o["nls"].double().mean().item()),
+            "flagged_elements": int((o["fl"] != 0).sum().item())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -416,6 +505,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
     ap.add_argument("--e2e-batch", type=int, default=512)
+    ap.add_argument("--chunks", type=int, default=1, help="sub-batches per GPU; >1 overlaps fwd(i+1) with bwd(i)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()

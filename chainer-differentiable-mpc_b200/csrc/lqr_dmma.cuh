@@ -323,6 +323,71 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
     __syncthreads();                                                     // (4)
     st ^= 1;
   }
+
+  // ---- fused rollout (lqr_recursion.py:160-200): the CTA re-streams K_t, k_t, F_t, f_t through a
+  //      3-deep cp.async ring carved from the (now dead) Riccati stage buffers.  While this CTA is in
+  //      its memory-bound rollout the other CTAs of the SM keep the DMMA pipe busy.
+  if (p.flags & LQR_DO_ROLLOUT) {
+    constexpr int RK = 0, Rk = RK + M * N, RF = Rk + M, Rf = RF + N * LDF, RSTG = Rf + N;   // 1704 doubles
+    static_assert(3 * RSTG <= 2 * Cfg::STG, "rollout ring must fit in the Riccati stages");
+    double* xcur = sm + Cfg::OV;           // [S]  (V is dead)
+    double* xnew = sm + Cfg::OV + 64;      // [N]
+    auto load_roll = [&](int t, int slot) {
+      double* base = sm + slot * RSTG;
+      const size_t idx = (size_t)t * tb + e;
+      for (int c = tid; c < M * N / 2; c += NT) cp_async16(base + RK + c * 2, p.Ks + idx * M * N + c * 2);
+      if (tid < M / 2) cp_async16(base + Rk + tid * 2, p.ks + idx * M + tid * 2);
+      if (t < T - 1) {
+        if (ld_active) {
+          const double* Fg = p.F + idx * N * S + ld_cc * 2;
+          double* Fd = base + RF + ld_cc * 2;
+          for (int r = ld_r0; r < N; r += LD_RSTEP) cp_async16(Fd + r * LDF, Fg + r * S);
+        }
+        if (have_f && tid >= 32 && tid < 32 + N / 2) cp_async16(base + Rf + (tid - 32) * 2, p.f + idx * N + (tid - 32) * 2);
+      }
+    };
+    // prologue: stages 0,1 (one commit group per timestep, empty groups keep the accounting uniform)
+    load_roll(0, 0); cp_async_commit();
+    if (T > 1) load_roll(1, 1);
+    cp_async_commit();
+    if (tid < N) xcur[tid] = p.x0[(size_t)e * N + tid];
+    for (int t = 0; t < T; ++t) {
+      if (t + 2 < T) load_roll(t + 2, (t + 2) % 3);
+      cp_async_commit();
+      cp_async_wait<2>();
+      __syncthreads();
+      const double* base = sm + (t % 3) * RSTG;
+      const double* Kt = base + RK; const double* kt = base + Rk; const double* Ft = base + RF; const double* ft = base + Rf;
+      {   // u = K x + k : 16 lanes per control
+        const int o = tid >> 4, part = tid & 15;
+        double a = Kt[o * N + 2 * part] * xcur[2 * part] + Kt[o * N + 2 * part + 1] * xcur[2 * part + 1];
+        a += __shfl_xor_sync(0xffffffffu, a, 8);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        if (part == 0) xcur[N + o] = a + kt[o];
+      }
+      __syncthreads();
+      {
+        const size_t idx = (size_t)t * tb + e;
+        if (tid < N) { if (p.x) p.x[idx * N + tid] = xcur[tid]; }
+        else if (tid < S) { if (p.u) p.u[idx * M + tid - N] = xcur[tid]; }
+        if (p.tau_out && tid < S) p.tau_out[idx * S + tid] = xcur[tid];
+      }
+      if (t < T - 1) {   // x' = F [x;u] + f : 4 lanes per state, interleaved split (conflict free with ld = S + 4)
+        const int i = tid >> 2, part = tid & 3;
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < S / 4; ++j) a += Ft[i * LDF + 4 * j + part] * xcur[4 * j + part];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (part == 0) xnew[i] = a + (have_f ? ft[i] : 0.0);
+        __syncthreads();
+        if (tid < N) xcur[tid] = xnew[tid];
+      }
+      __syncthreads();
+    }
+  }
 }
 
 }  // namespace dmpc

@@ -55,9 +55,9 @@ static int launch_lqr_solve_dmma(const LqrParams<double>& p, cudaStream_t st, lo
     const size_t smem = (size_t)Cfg::TOTAL * sizeof(double);
     auto kern = lqr_factor_dmma_kernel<32, 8>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DMPC_ERR_CUDA;
-    kern<<<p.B, Cfg::NT, smem, st>>>(p);
+    kern<<<p.B, Cfg::NT, smem, st>>>(p);          // the rollout (if requested) is fused into the same launch
     if (nl) ++*nl;
-    if (cudaGetLastError() != cudaSuccess) return DMPC_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
   }
   if (p.flags & LQR_DO_ROLLOUT) {
     LqrParams<double> q = p;
