@@ -21,6 +21,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// Shared-memory fragment load that the compiler may not sink below later volatile asm (the DMMAs):
+// lets the kernel issue the loads of k-step i+1 before the DMMAs of k-step i.
+__device__ __forceinline__ double lds_f64(const double* p) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
+
 // 1/x to ~1 ulp: MUFU seed (20 bits) + two Newton steps; the LU only needs a good reciprocal
 // (LAPACK dgetf2 also scales by the reciprocal of the pivot).
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -83,6 +91,110 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Phase B work of warp W in {1,2,3} (warp 0 inverts Quu meanwhile):
+//   P1'  Mx[:, :n] = V F[:, :n]: row block W (4 tiles) + a share of row block 0
+//        (W=1: column blocks 0,1; W=2: 2; W=3: 3)
+//   P2'  Q = C + F^T Mx except tile (u,u): row block W (5 tiles) + tiles 3(W-1)..3(W-1)+2 of
+//        [(0,0) (0,1) (0,2) (0,3) (0,4) (4,0) (4,1) (4,2) (4,3)]
+// Tile ownership is compile-time so that all fragments live in registers; fragment loads are
+// volatile and issued one k-step ahead of the DMMAs that consume them.
+template <int N, int M, int W>
+__device__ __forceinline__ void phase_b_tiles(const double* V, double* Mx, const double* Ft, double* Q, double* q,
+                                              const double* mv, int tid, int gr, int tg) {
+  using Cfg = DmmaCfg<N, M>;
+  constexpr int S = Cfg::S, NB = Cfg::NB, NT = Cfg::NT, LDV = Cfg::LDV, LDF = Cfg::LDF;
+  constexpr int NX = (W == 1) ? 2 : 1;              // row-block-0 tiles of this warp
+  constexpr int JX0 = (W == 1) ? 0 : W;             // their first column block
+  // ---------------- P1'
+  {
+    double acc[NB][2], accx[NX][2];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < NX; ++j) { accx[j][0] = 0.0; accx[j][1] = 0.0; }
+    const double* Va = V + (W * 8 + gr) * LDV + tg;
+    const double* V0 = V + gr * LDV + tg;
+    const double* Fb = Ft + tg * LDF + gr;
+    double a = lds_f64(Va), a0 = lds_f64(V0), b[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) b[j] = lds_f64(Fb + j * 8);
+#pragma unroll
+    for (int k0 = 0; k0 < N; k0 += 4) {
+      double an = 0.0, a0n = 0.0, bn[NB];
+      if (k0 + 4 < N) {
+        an = lds_f64(Va + k0 + 4); a0n = lds_f64(V0 + k0 + 4);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) bn[j] = lds_f64(Fb + (k0 + 4) * LDF + j * 8);
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) dmma884(acc[j][0], acc[j][1], a, b[j]);
+#pragma unroll
+      for (int j = 0; j < NX; ++j) dmma884(accx[j][0], accx[j][1], a0, b[JX0 + j]);
+      if (k0 + 4 < N) {
+        a = an; a0 = a0n;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) b[j] = bn[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      *reinterpret_cast<double2*>(Mx + (W * 8 + gr) * LDF + j * 8 + tg * 2) = make_double2(acc[j][0], acc[j][1]);
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+      *reinterpret_cast<double2*>(Mx + gr * LDF + (JX0 + j) * 8 + tg * 2) = make_double2(accx[j][0], accx[j][1]);
+  }
+  named_bar_sync(1, NT - 32);                  // Mx complete among warps 1..3 (VFu came through barrier (1))
+  // ---------------- P2'
+  {
+    constexpr int XI[3] = {(3 * (W - 1) + 0 < 5) ? 0 : NB, (3 * (W - 1) + 1 < 5) ? 0 : NB, (3 * (W - 1) + 2 < 5) ? 0 : NB};
+    constexpr int XJ[3] = {(3 * (W - 1) + 0 < 5) ? 3 * (W - 1) + 0 : 3 * (W - 1) + 0 - 5,
+                           (3 * (W - 1) + 1 < 5) ? 3 * (W - 1) + 1 : 3 * (W - 1) + 1 - 5,
+                           (3 * (W - 1) + 2 < 5) ? 3 * (W - 1) + 2 : 3 * (W - 1) + 2 - 5};
+    double acc[NB + 1][2], ex[3][2];
+#pragma unroll
+    for (int j = 0; j <= NB; ++j) {
+      const double2 c2 = *reinterpret_cast<const double2*>(Q + (W * 8 + gr) * LDF + j * 8 + tg * 2);
+      acc[j][0] = c2.x; acc[j][1] = c2.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double2 c2 = *reinterpret_cast<const double2*>(Q + (XI[j] * 8 + gr) * LDF + XJ[j] * 8 + tg * 2);
+      ex[j][0] = c2.x; ex[j][1] = c2.y;
+    }
+    const double* Fa = Ft + tg * LDF + gr;          // F^T fragments: row block r -> Fa[k0*LDF + 8 r]
+    const double* Mb = Mx + tg * LDF + gr;
+    double a = lds_f64(Fa + W * 8), a0 = lds_f64(Fa), au = lds_f64(Fa + NB * 8), b[NB + 1];
+#pragma unroll
+    for (int j = 0; j <= NB; ++j) b[j] = lds_f64(Mb + j * 8);
+#pragma unroll
+    for (int k0 = 0; k0 < N; k0 += 4) {
+      double an = 0.0, a0n = 0.0, aun = 0.0, bn[NB + 1];
+      if (k0 + 4 < N) {
+        an = lds_f64(Fa + (k0 + 4) * LDF + W * 8); a0n = lds_f64(Fa + (k0 + 4) * LDF); aun = lds_f64(Fa + (k0 + 4) * LDF + NB * 8);
+#pragma unroll
+        for (int j = 0; j <= NB; ++j) bn[j] = lds_f64(Mb + (k0 + 4) * LDF + j * 8);
+      }
+#pragma unroll
+      for (int j = 0; j <= NB; ++j) dmma884(acc[j][0], acc[j][1], a, b[j]);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) dmma884(ex[j][0], ex[j][1], XI[j] == 0 ? a0 : au, b[XJ[j]]);
+      if (k0 + 4 < N) {
+        a = an; a0 = a0n; au = aun;
+#pragma unroll
+        for (int j = 0; j <= NB; ++j) b[j] = bn[j];
+      }
+    }
+    // every Q tile is read and written by one warp only -> in-place stores need no barrier
+#pragma unroll
+    for (int j = 0; j <= NB; ++j)
+      *reinterpret_cast<double2*>(Q + (W * 8 + gr) * LDF + j * 8 + tg * 2) = make_double2(acc[j][0], acc[j][1]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      *reinterpret_cast<double2*>(Q + (XI[j] * 8 + gr) * LDF + XJ[j] * 8 + tg * 2) = make_double2(ex[j][0], ex[j][1]);
+  }
+}
+
+
 // warp-level 8x8 output tile: acc += A(8 x K) * B(K x 8), fragments fetched by the given functors
 #define DMPC_TILE_LOOP(acc0, acc1, K, AEXPR, BEXPR)            \
   _Pragma("unroll") for (int k0 = 0; k0 < (K); k0 += 4) {      \
@@ -131,10 +243,13 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
   };
 
   load_tiles(T - 1, 0);
+  cp_async_wait<0>();
+  __syncthreads();
   int st = 0;
   for (int t = T - 1; t >= 0; --t) {
-    if (t > 0) { load_tiles(t - 1, st ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();                                                     // (0)
+    // tiles of step t are resident (waited for before the barrier that closed step t+1);
+    // prefetch step t-1 into the other stage
+    if (t > 0) load_tiles(t - 1, st ^ 1);
     double* base = sm + st * Cfg::STG;
     double* Q = base + Cfg::OC;        // C_t, overwritten in place by Q_t
     double* q = base + Cfg::Oc;        // c_t -> q_t
@@ -192,80 +307,28 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
 #pragma unroll
         for (int i = 0; i < M; ++i) { Qi[i * LDQI + lane - M] = c[i]; if (fg) fg[i * M + lane - M] = c[i]; }
       }
-    } else if (t < T - 1) {
-      const int w = warp - 1;                      // 0..2
-      // Mx[:, :n] = V F[:, :n] : row block `warp` (4 tiles) + a share of row block 0
-      {
-        double acc[NB][2];
+      if (t < T - 1) {
+        // q = c + F^T mv (in place on the staged c): warp 0 has slack after the inverse
 #pragma unroll
-        for (int jb = 0; jb < NB; ++jb) { acc[jb][0] = 0.0; acc[jb][1] = 0.0; }
-#pragma unroll 4
-        for (int k0 = 0; k0 < N; k0 += 4) {
-          const double a = V[(warp * 8 + gr) * LDV + k0 + tg];
-#pragma unroll
-          for (int jb = 0; jb < NB; ++jb) dmma884(acc[jb][0], acc[jb][1], a, Ft[(k0 + tg) * LDF + jb * 8 + gr]);
-        }
-#pragma unroll
-        for (int jb = 0; jb < NB; ++jb)
-          *reinterpret_cast<double2*>(Mx + (warp * 8 + gr) * LDF + jb * 8 + tg * 2) = make_double2(acc[jb][0], acc[jb][1]);
-        // row block 0: warp 1 -> column blocks 0,1 ; warp 2 -> 2 ; warp 3 -> 3
-        const int jb0 = (w == 0) ? 0 : w + 1;
-        double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
-#pragma unroll 4
-        for (int k0 = 0; k0 < N; k0 += 4) {
-          const double a = V[gr * LDV + k0 + tg];
-          dmma884(x0, x1, a, Ft[(k0 + tg) * LDF + jb0 * 8 + gr]);
-          if (w == 0) dmma884(y0, y1, a, Ft[(k0 + tg) * LDF + 8 + gr]);
-        }
-        *reinterpret_cast<double2*>(Mx + gr * LDF + jb0 * 8 + tg * 2) = make_double2(x0, x1);
-        if (w == 0) *reinterpret_cast<double2*>(Mx + gr * LDF + 8 + tg * 2) = make_double2(y0, y1);
-      }
-      named_bar_sync(1, NT - 32);                  // Mx complete among warps 1..3 (VFu came through (1))
-      // Q = C + F^T Mx except tile (u,u): row block `warp` (5 tiles) + 3 more tiles per warp
-      {
-        double acc[NB + 1][2];
-#pragma unroll
-        for (int jb = 0; jb <= NB; ++jb) {
-          const double2 c2 = *reinterpret_cast<const double2*>(Q + (warp * 8 + gr) * LDF + jb * 8 + tg * 2);
-          acc[jb][0] = c2.x; acc[jb][1] = c2.y;
-        }
-        // extra tiles: id = 3 w + j over [(0,0) (0,1) (0,2) (0,3) (0,4) (4,0) (4,1) (4,2) (4,3)]
-        int xi[3], xj[3];
-        double ex[3][2];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int id = 3 * w + j;
-          xi[j] = (id < 5) ? 0 : NB;
-          xj[j] = (id < 5) ? id : id - 5;
-          const double2 c2 = *reinterpret_cast<const double2*>(Q + (xi[j] * 8 + gr) * LDF + xj[j] * 8 + tg * 2);
-          ex[j][0] = c2.x; ex[j][1] = c2.y;
-        }
-#pragma unroll 4
-        for (int k0 = 0; k0 < N; k0 += 4) {
-          const double a = Ft[(k0 + tg) * LDF + warp * 8 + gr];
-#pragma unroll
-          for (int jb = 0; jb <= NB; ++jb) dmma884(acc[jb][0], acc[jb][1], a, Mx[(k0 + tg) * LDF + jb * 8 + gr]);
-#pragma unroll
-          for (int j = 0; j < 3; ++j)
-            dmma884(ex[j][0], ex[j][1], Ft[(k0 + tg) * LDF + xi[j] * 8 + gr], Mx[(k0 + tg) * LDF + xj[j] * 8 + gr]);
-        }
-        // q = c + F^T mv (reads c in place) on the 96 threads of warps 1..3
-        for (int o = tid - 32; o < S * 4; o += NT - 32) {
+        for (int o = lane; o < S * 4; o += 32) {
           const int i = o >> 2, part = o & 3;
-          double sacc = 0.0;
+          double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-          for (int k = 0; k < N / 4; ++k) sacc += Ft[(4 * k + part) * LDF + i] * mv[4 * k + part];
+          for (int k = 0; k < N / 4; k += 2) {
+            s0 += Ft[(4 * k + part) * LDF + i] * mv[4 * k + part];
+            s1 += Ft[(4 * k + 4 + part) * LDF + i] * mv[4 * k + 4 + part];
+          }
+          double sacc = s0 + s1;
           sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
           sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
           if (part == 0) q[i] += sacc;
         }
-        // every Q tile is read and written by one warp only -> in-place stores need no barrier
-#pragma unroll
-        for (int jb = 0; jb <= NB; ++jb)
-          *reinterpret_cast<double2*>(Q + (warp * 8 + gr) * LDF + jb * 8 + tg * 2) = make_double2(acc[jb][0], acc[jb][1]);
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          *reinterpret_cast<double2*>(Q + (xi[j] * 8 + gr) * LDF + xj[j] * 8 + tg * 2) = make_double2(ex[j][0], ex[j][1]);
+      }
+    } else if (t < T - 1) {
+      switch (warp) {
+        case 1: phase_b_tiles<N, M, 1>(V, Mx, Ft, Q, q, mv, tid, gr, tg); break;
+        case 2: phase_b_tiles<N, M, 2>(V, Mx, Ft, Q, q, mv, tid, gr, tg); break;
+        default: phase_b_tiles<N, M, 3>(V, Mx, Ft, Q, q, mv, tid, gr, tg); break;
       }
     }
     __syncthreads();                                                     // (2)
@@ -320,7 +383,8 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
         }
       }
     }
-    __syncthreads();                                                     // (4)
+    cp_async_wait<0>();                                                  // tiles of step t-1 have landed
+    __syncthreads();                                                     // (4) closes step t and publishes them
     st ^= 1;
   }
 
