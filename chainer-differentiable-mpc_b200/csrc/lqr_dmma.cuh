@@ -214,10 +214,12 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
   double* Kk = sm + Cfg::OKk; double* Pm = sm + Cfg::OP; double* Qi = sm + Cfg::OQi;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gr = lane >> 2, tg = lane & 3;
   const int T = p.T, B = p.B;
-  const int e = blockIdx.x;
   const size_t tb = (size_t)B;
   const bool have_f = p.f != nullptr;
   const bool save_fac = (p.flags & LQR_SAVE_FAC) && p.fac;
+  // persistent CTAs: the grid is (CTAs per SM) x (SMs) and every CTA strides over the batch, so the
+  // launch can leave shared memory free for a memory-bound kernel running beside it (bench.py --chunks)
+  for (int e = blockIdx.x; e < B; e += gridDim.x) {
   // per-thread 16-byte chunk of a row: 20 chunks per row of S doubles, 6 rows in flight per pass
   const int ld_cc = tid % (S / 2), ld_r0 = tid / (S / 2);
   constexpr int LD_RSTEP = NT / (S / 2);          // 6 full rows per pass (threads >= 120 idle)
@@ -452,6 +454,8 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
       __syncthreads();
     }
   }
+  __syncthreads();
+  }   // element loop
 }
 
 }  // namespace dmpc

@@ -55,7 +55,17 @@ static int launch_lqr_solve_dmma(const LqrParams<double>& p, cudaStream_t st, lo
     const size_t smem = (size_t)Cfg::TOTAL * sizeof(double);
     auto kern = lqr_factor_dmma_kernel<32, 8>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DMPC_ERR_CUDA;
-    kern<<<p.B, Cfg::NT, smem, st>>>(p);          // the rollout (if requested) is fused into the same launch
+    static int n_sm = 0;
+    if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    // default: one CTA per element (the hardware back-fills 3 CTAs per SM).  DMPC_FACTOR_CTAS_PER_SM=k makes
+    // the grid persistent with k CTAs per SM striding over the batch (k=2 leaves shared memory for a
+    // co-running kernel; measured slower on its own).
+    int grid = p.B;
+    if (const char* e = getenv("DMPC_FACTOR_CTAS_PER_SM")) {
+      const int v = atoi(e);
+      if (v >= 1 && v <= 3 && p.B > v * n_sm) grid = v * n_sm;
+    }
+    kern<<<grid, Cfg::NT, smem, st>>>(p);          // persistent CTAs; the rollout (if requested) is fused in
     if (nl) ++*nl;
     return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
   }
