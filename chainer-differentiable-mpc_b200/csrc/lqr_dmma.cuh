@@ -1,15 +1,17 @@
 // Large-state Riccati sweep on the FP64 tensor path (DMMA, mma.sync.m8n8k4.f64) for sm_100a.
 //
-// BASELINE config 5 (n=32, m=8, T=100): F^T V F is a real dense contraction (73 % of the flops),
-// so it runs on DMMA; tcgen05 has no f64 kind.  One CTA of (n+m)/8 warps owns one
-// batch element for the whole horizon; warp w owns column block w of every tile product:
-//     P1  Mx = V F_t                    (n x s,  K = n)     mv = V f_t + v
-//     P2  Q  = C_t + F_t^T Mx  (in place on the staged C_t)  q  = c_t + F_t^T mv
-//     LU  warp 0: in-register pivoted LU of Quu carrying [-Qux | -qu | I] -> K_t, k_t, Quu^-1
-//     P3  P = [Qux|qu] + Quu [K|k];  V = Qxx + Qxu K + K^T P;  v likewise
-// (reference lqr/lqr_recursion.py:79-152).  Tiles are streamed with 16-byte cp.async into a
-// double-buffered stage with padded leading dimensions (ld = 4 mod 8 doubles) so that every DMMA
-// fragment load is shared-memory bank-conflict free.
+// BASELINE config 5 (n=32, m=8, T=100): F^T V F is a real dense contraction (73 % of the flops), so it runs
+// on DMMA; tcgen05 has no f64 kind.  One CTA of four warps owns one batch element for the
+// whole horizon (reference lqr/lqr_recursion.py:79-152):
+//     A    all warps : V F[:, n:] (one row block each)               mv = V f_t + v
+//     B    warp 0    : Quu = Cuu + Fu^T (V Fu); Gauss-Jordan inverse of the 8 x 8 block in registers;
+//                      q = c_t + F_t^T mv
+//          warps 1-3 : the other 16 tiles of Mx = V F_t and 24 tiles of Q = C_t + F_t^T Mx (in place on the
+//                      staged C_t) - the inverse is hidden behind this work
+//     C+D  all warps : K = -Quu^-1 Qux (DMMA), k = -Quu^-1 qu, V = Qxx + Qxu K, v = qx + Qxu k
+// then (optionally) the rollout x_{t+1} = F_t [x_t; K_t x_t + k_t] + f_t through a 3-deep cp.async ring.
+// Tiles are streamed with 16-byte cp.async into a double-buffered stage with padded leading dimensions
+// (ld = 4 mod 8 doubles) so that every DMMA fragment load is shared-memory bank-conflict free.
 #pragma once
 #include "common.cuh"
 #include "lqr_kernels.cuh"
@@ -47,9 +49,9 @@ struct DmmaCfg {
   static constexpr int OC = 0, Oc = OC + S * LDF, OF = Oc + S, Of = OF + N * LDF, STG = Of + N;
   static constexpr int OV = 2 * STG, Ov = OV + N * LDV, OMx = Ov + N, Omv = OMx + N * LDF, OQi = Omv + N,
                        TOTAL = OQi + M * LDQI;
-  static constexpr int OKk = OMx, OP = OMx + M * LDK;     // alias the dead Mx region after P2
+  static constexpr int OKk = OMx;     // K_t tile aliases the Mx region, dead after phase B
   static_assert(M == 8 && N == 32, "DMMA path is instantiated for n = 32, m = 8");
-  static_assert(2 * M * LDK <= N * LDF, "Kk/P alias must fit in Mx");
+  static_assert(M * LDK <= N * LDF, "Kk alias must fit in Mx");
   static_assert(STG % 2 == 0 && OV % 2 == 0 && OMx % 2 == 0 && OQi % 2 == 0, "16B alignment");
 };
 
@@ -99,10 +101,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // Tile ownership is compile-time so that all fragments live in registers; fragment loads are
 // volatile and issued one k-step ahead of the DMMAs that consume them.
 template <int N, int M, int W>
-__device__ __forceinline__ void phase_b_tiles(const double* V, double* Mx, const double* Ft, double* Q, double* q,
-                                              const double* mv, int tid, int gr, int tg) {
+__device__ __forceinline__ void phase_b_tiles(const double* V, double* Mx, const double* Ft, double* Q, int gr, int tg) {
   using Cfg = DmmaCfg<N, M>;
-  constexpr int S = Cfg::S, NB = Cfg::NB, NT = Cfg::NT, LDV = Cfg::LDV, LDF = Cfg::LDF;
+  constexpr int NB = Cfg::NB, NT = Cfg::NT, LDV = Cfg::LDV, LDF = Cfg::LDF;
   constexpr int NX = (W == 1) ? 2 : 1;              // row-block-0 tiles of this warp
   constexpr int JX0 = (W == 1) ? 0 : W;             // their first column block
   // ---------------- P1'
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   double* V = sm + Cfg::OV; double* v = sm + Cfg::Ov; double* Mx = sm + Cfg::OMx; double* mv = sm + Cfg::Omv;
-  double* Kk = sm + Cfg::OKk; double* Pm = sm + Cfg::OP; double* Qi = sm + Cfg::OQi;
+  double* Kk = sm + Cfg::OKk; double* Qi = sm + Cfg::OQi;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gr = lane >> 2, tg = lane & 3;
   const int T = p.T, B = p.B;
   const size_t tb = (size_t)B;
@@ -328,9 +329,9 @@ __global__ void __launch_bounds__(DmmaCfg<N, M>::NT, 3) lqr_factor_dmma_kernel(L
       }
     } else if (t < T - 1) {
       switch (warp) {
-        case 1: phase_b_tiles<N, M, 1>(V, Mx, Ft, Q, q, mv, tid, gr, tg); break;
-        case 2: phase_b_tiles<N, M, 2>(V, Mx, Ft, Q, q, mv, tid, gr, tg); break;
-        default: phase_b_tiles<N, M, 3>(V, Mx, Ft, Q, q, mv, tid, gr, tg); break;
+        case 1: phase_b_tiles<N, M, 1>(V, Mx, Ft, Q, gr, tg); break;
+        case 2: phase_b_tiles<N, M, 2>(V, Mx, Ft, Q, gr, tg); break;
+        default: phase_b_tiles<N, M, 3>(V, Mx, Ft, Q, gr, tg); break;
       }
     }
     __syncthreads();                                                     // (2)

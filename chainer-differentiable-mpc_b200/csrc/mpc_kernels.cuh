@@ -48,10 +48,6 @@ __device__ __forceinline__ R qp_objective(const R* H, int ldh, const R* q, const
   return R(0.5) * quad + lin;
 }
 
-struct PnqpWork {   // offsets (in reals) inside the caller's shared-memory region
-  int Hf, rhs, g, dx, xh, x, piv;
-};
-
 // Projected-Newton box QP for ONE element, executed by the SG (<=32) lanes of `sg`.
 //   H[m x m] (ld ldh), q, lo, hi: shared memory, read-only.  x: in = clamped start, out = solution.
 //   On return Hf holds the LU of the last masked Hessian (+REG I), piv its pivots.

@@ -28,13 +28,13 @@ class DiffLqr(FunctionNodeBase):
     """`DiffLqr(T, n_batch, n_state, n_ctrl).apply((x_init, C, c, F, f)) -> (x, u)`."""
 
     def __init__(self, T, n_batch, n_state, n_ctrl, device=0, dtype=np.float64, strict_reference=True,
-                 pinned_outputs=False):
+                 pinned_outputs=False, context=None):
         super().__init__()
         self.T, self.n_batch, self.n_state, self.n_ctrl = int(T), int(n_batch), int(n_state), int(n_ctrl)
         self.n_sc = self.n_state + self.n_ctrl
         self.dtype = np.dtype(dtype)
         self.strict_reference = strict_reference
-        self._ctx = _native.default_context(device)
+        self._ctx = context if context is not None else _native.default_context(device)
         self._d = None
         self._pinned = pinned_outputs
         self._host = {}
