@@ -1,0 +1,366 @@
+// Large-state Riccati sweep, second generation: ONE WARP owns one batch element and keeps the whole
+// recursion state in DMMA fragment registers (sm_100a, mma.sync.m8n8k4.f64).
+//
+// Why: the CTA-per-element kernel (lqr_dmma.cuh) fetches every DMMA operand from shared memory and is bound
+// by the shared-memory pipe (ncu r1f: l1tex data-pipe wavefronts 70 % of peak, 2995 wavefronts per
+// element-step against 1600 DMMA-pipe cycles).  Here the operands stay in registers:
+//
+//   * the accumulator layout of a DMMA output tile (lane (g,t) holds D[g][2t], D[g][2t+1]) IS a valid
+//     B (or A) fragment of the next product if the contraction index inside each 8-block is enumerated
+//     in the order k(t,e) = 2t+e.  A contraction is invariant under a permutation of k applied to both
+//     operands, so V_t (accumulators of step t+1) feeds step t directly, W^T = F^T V^T feeds Q = C + F^T W,
+//     and Qxu feeds V = Qxx + Qxu K - no shared-memory round trip, no layout conversion.
+//   * the only fragments read from shared memory are those of F_t (staged by cp.async, two reads per
+//     element: once for W^T, once for Q) and the 8-row K/Qux/Quu^-1 panels of the gain computation.
+//   * C_t never touches shared memory: it is the accumulator initialiser of Q and is loaded straight
+//     into the accumulator registers (LDG.128, one row block ahead).
+//
+// Per step (reference lqr/lqr_recursion.py:79-152), all by one warp:
+//     mv   = V f_t + v                                   (FMA + 2 shuffles)
+//     W^T  = F_t^T V^T                       160 DMMA    (A = F fragments, B = V registers)
+//     Q    = C_t + F_t^T W, q = c_t + F_t^T mv   200 DMMA (A = F fragments, B = W^T registers), row block u first
+//     Quu^-1 by in-register Gauss-Jordan (warp_gj_inverse), K = -Quu^-1 Qux (8 DMMA), k = -Quu^-1 qu
+//     V    = Qxx + Qxu K, v = qx + Qxu k      32 DMMA    (A = Qxu registers, accumulate in place on Qxx)
+// then (optionally) the rollout x_{t+1} = F_t [x_t; K_t x_t + k_t] + f_t.  Warps never synchronise with each
+// other; 8 warps per SM (255 registers each) keep two independent recursions on every DMMA pipe.
+#pragma once
+#include "common.cuh"
+#include "lqr_kernels.cuh"
+#include "lqr_dmma.cuh"
+
+namespace dmpc {
+
+// DMMA as a pure function of its operands (non-volatile: ptxas may schedule loads around it)
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double quad_sum(double a) {      // sum over the 4 lanes t = 0..3 of a row group
+  a += __shfl_xor_sync(0xffffffffu, a, 1);
+  a += __shfl_xor_sync(0xffffffffu, a, 2);
+  return a;
+}
+
+struct WarpCfg {
+  static constexpr int N = 32, M = 8, S = 40;
+  // F buffer: row pitch 42 doubles -> the four fragment rows 2t+e of a half-warp fall in distinct 32-byte
+  // bank groups (4*LDF = 8 mod 32).  C buffer: dense (pitch 40), read as accumulator tiles (16 B per lane).
+  static constexpr int LDF = 42;
+  static constexpr int OF = 0, Of = OF + N * LDF, Oc = Of + N, OC = Oc + S, OSCR = OC + S * S;
+  // per-warp scratch
+  static constexpr int LDQ = 36;     // Qux panel [8][36]: B fragments by rows k0+t
+  static constexpr int LDU = 12;     // Quu / Quu^-1 [8][12]: A fragments by rows g
+  static constexpr int LDK = 34;     // K panel [8][34]: B fragments by rows 2t+e (aliases the Qux panel)
+  static constexpr int OQux = OSCR, OK = OQux, OQuu = OQux + M * LDQ, OQi = OQuu + M * LDU, Omv = OQi,
+                       Oqu = OQi + M * LDU, Okk = Oqu + M, TOTAL = Okk + M;
+  // rollout: two stages {F, f, K_t [8][36], k_t} carved from the same region, then x|u and x_next
+  static constexpr int LDKR = 36;
+  static constexpr int RF = 0, Rf = RF + N * LDF, RK = Rf + N, Rk = RK + M * LDKR, RSTG = Rk + M;
+  static constexpr int Oxs = 2 * RSTG, Oxn = Oxs + S;
+  static_assert(Oxn + N <= TOTAL, "rollout buffers must fit");
+  static_assert(M * LDK <= M * LDQ && N <= M * LDU, "aliases must fit");
+  static_assert(Of % 2 == 0 && Oc % 2 == 0 && OC % 2 == 0 && OSCR % 2 == 0 && OQuu % 2 == 0 && OQi % 2 == 0 &&
+                Oqu % 2 == 0 && Okk % 2 == 0 && RSTG % 2 == 0 && Rf % 2 == 0 && RK % 2 == 0 && Rk % 2 == 0, "16-byte alignment");
+};
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void* g, unsigned bytes) {   // bytes % 16 == 0, g 16-byte aligned
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(g), "r"(bytes) : "memory");
+}
+
+// F_t ([32][40] contiguous in global memory) -> padded rows in shared memory, 20 x 16-byte chunks per lane.
+// Chunk q = 32 it + lane lies in row q / 20: with lane = 20 rl + cl that is a_it + rl + (cl >= 20 - b_it) for
+// the compile-time split 32 it = 20 a_it + b_it - no division and nothing to keep in registers.
+__device__ __forceinline__ void stage_F(double* Fs, const double* Fg, int lane) {
+  constexpr int LDF = WarpCfg::LDF;
+  const int rl = lane >= 20 ? 1 : 0, cl = lane - 20 * rl;
+#pragma unroll
+  for (int it = 0; it < 20; ++it) {
+    const int a = (32 * it) / 20, b = (32 * it) % 20;
+    const int row = a + rl + ((cl >= 20 - b) ? 1 : 0);
+    const int q = 32 * it + lane;
+    cp_async16(Fs + q * 2 + row * (LDF - 40), Fg + q * 2);
+  }
+}
+
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel(LqrParams<double> p) {
+  using Cfg = WarpCfg;
+  constexpr int N = Cfg::N, M = Cfg::M, S = Cfg::S, LDF = Cfg::LDF, LDQ = Cfg::LDQ, LDU = Cfg::LDU, LDK = Cfg::LDK;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gr = lane >> 2, tg = lane & 3;
+  const int T = p.T, B = p.B;
+  const int e = blockIdx.x * WPC + warp;
+  if (e >= B) return;                       // warps are independent: no CTA-wide barrier anywhere below
+  double* sm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * Cfg::TOTAL;
+  const size_t tb = (size_t)B;
+  const bool have_f = p.f != nullptr;
+  const bool save_fac = (p.flags & LQR_SAVE_FAC) && p.fac;
+
+  if (p.flags & LQR_DO_FACTOR) {
+    double* Fs = sm + Cfg::OF; double* fs = sm + Cfg::Of; double* cs = sm + Cfg::Oc; double* Cs = sm + Cfg::OC;
+    double* Qux_s = sm + Cfg::OQux; double* Quu_s = sm + Cfg::OQuu; double* Qi_s = sm + Cfg::OQi;
+    double* K_s = sm + Cfg::OK; double* qu_s = sm + Cfg::Oqu; double* kk_s = sm + Cfg::Okk; double* mv_s = sm + Cfg::Omv;
+
+    // Single-buffered, refilled just in time: a row block of C_{t-1} is requested as soon as pass i of step t has
+    // read its accumulators (a full step ahead of its use); F_{t-1}, f_{t-1}, c_{t-1} are requested after the last
+    // Q pass and land behind the gain computation - from L2, where a bulk prefetch issued one step earlier put them.
+    auto stage_C_rows = [&](int t, int i) {
+      const double* Cg = p.C + ((size_t)t * tb + e) * (S * S) + i * 8 * S;
+#pragma unroll
+      for (int it = 0; it < 8 * S / 64; ++it) cp_async16(Cs + i * 8 * S + (it * 32 + lane) * 2, Cg + (it * 32 + lane) * 2);
+    };
+    auto stage_Ffc = [&](int t) {
+      const size_t idx = (size_t)t * tb + e;
+      if (t < T - 1) {
+        stage_F(Fs, p.F + idx * (N * S), lane);
+        if (have_f && lane < N / 2) cp_async16(fs + lane * 2, p.f + idx * N + lane * 2);
+      }
+      if (lane < S / 2) cp_async16(cs + lane * 2, p.c + idx * S + lane * 2);
+    };
+
+    // V_t as accumulator-layout registers: Vr[r][kb][e] = V[8r+g][8kb+2t+e];  vr[r] = v[8r+g]
+    double Vr[4][4][2];
+    double vr[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      vr[r] = 0.0;
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) { Vr[r][kb][0] = 0.0; Vr[r][kb][1] = 0.0; }
+    }
+
+#pragma unroll
+    for (int i = 0; i < 5; ++i) stage_C_rows(T - 1, i);
+    stage_Ffc(T - 1);
+    cp_async_commit();
+    if (T > 1 && lane == 0) l2_prefetch_bulk(p.F + ((size_t)(T - 2) * tb + e) * (N * S), N * S * 8);
+
+    for (int t = T - 1; t >= 0; --t) {
+      cp_async_wait<0>();
+      __syncwarp();                                    // C_t, F_t, f_t, c_t are resident
+      if (t > 1 && lane == 0) l2_prefetch_bulk(p.F + ((size_t)(t - 2) * tb + e) * (N * S), N * S * 8);
+      const size_t idx = (size_t)t * tb + e;
+      const bool last = (t == T - 1);
+
+      double WT[5][4][2];          // WT[j][r][e] = W[8r+2t+e][8j+g],  W = V F
+      if (!last) {
+        // ---- mv = V f + v
+        double mvr[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          double a = 0.0;
+          if (have_f) {
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+              const double2 f2 = *reinterpret_cast<const double2*>(fs + kb * 8 + 2 * tg);
+              a = __fma_rn(Vr[r][kb][0], f2.x, a);
+              a = __fma_rn(Vr[r][kb][1], f2.y, a);
+            }
+            a = quad_sum(a);
+          }
+          mvr[r] = a + vr[r];
+        }
+        if (tg == 0) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) mv_s[r * 8 + gr] = mvr[r];
+        }
+        // ---- W^T = F^T V^T : tile (j, r) = sum_k F[k][8j+g] * V[8r+g'][k],  k = 8kb+2t+e
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          double a[4][2];
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            a[kb][0] = Fs[(kb * 8 + 2 * tg) * LDF + j * 8 + gr];
+            a[kb][1] = Fs[(kb * 8 + 2 * tg + 1) * LDF + j * 8 + gr];
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) { WT[j][r][0] = 0.0; WT[j][r][1] = 0.0; }
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+            for (int ee = 0; ee < 2; ++ee)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) dmma(WT[j][r], a[kb][ee], Vr[r][kb][ee]);
+        }
+        __syncwarp();                                  // mv_s complete
+      }
+
+      // ---- Q = C + F^T W (row block u first), q = c + F^T mv
+      double Qxx[4][4][2], Qxu[4][2], qx[4];
+#pragma unroll
+      for (int pi = 0; pi < 5; ++pi) {
+        const int i = (pi == 0) ? 4 : pi - 1;
+        double acc[5][2];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const double2 c2 = *reinterpret_cast<const double2*>(Cs + (i * 8 + gr) * S + j * 8 + 2 * tg);
+          acc[j][0] = c2.x; acc[j][1] = c2.y;
+        }
+        __syncwarp();
+        if (t > 0) stage_C_rows(t - 1, i);             // refill this row block for the next step
+        double qa = 0.0;
+        if (!last) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const double2 m2 = *reinterpret_cast<const double2*>(mv_s + r * 8 + 2 * tg);
+#pragma unroll
+            for (int ee = 0; ee < 2; ++ee) {
+              const double a = Fs[(r * 8 + 2 * tg + ee) * LDF + i * 8 + gr];
+#pragma unroll
+              for (int j = 0; j < 5; ++j) dmma(acc[j], a, WT[j][r][ee]);
+              qa = __fma_rn(a, ee ? m2.y : m2.x, qa);
+            }
+          }
+          qa = quad_sum(qa);
+        }
+        qa += cs[i * 8 + gr];
+        if (i == 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<double2*>(Qux_s + gr * LDQ + j * 8 + 2 * tg) = make_double2(acc[j][0], acc[j][1]);
+          *reinterpret_cast<double2*>(Quu_s + gr * LDU + 2 * tg) = make_double2(acc[4][0], acc[4][1]);
+          if (tg == 0) qu_s[gr] = qa;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { Qxx[i][j][0] = acc[j][0]; Qxx[i][j][1] = acc[j][1]; }
+          Qxu[i][0] = acc[4][0]; Qxu[i][1] = acc[4][1];
+          qx[i] = qa;
+        }
+      }
+      __syncwarp();                                    // F_t, f_t, c_t, mv are dead; Qux, Quu, qu are complete
+      if (t > 0) { stage_Ffc(t - 1); cp_async_commit(); }
+
+      // ---- Quu^-1 (Gauss-Jordan, partial pivoting; lanes 8..15 end up with its columns)
+      double* fg = save_fac ? p.fac + idx * (M * M + N * M) : nullptr;
+      {
+        double cinv[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) cinv[i] = (lane < M) ? Quu_s[i * LDU + lane] : ((lane - M == i) ? 1.0 : 0.0);
+        warp_gj_inverse<M>(cinv);
+        if (lane >= M && lane < 2 * M) {               // (Qi aliases mv, dead since the barrier above)
+#pragma unroll
+          for (int i = 0; i < M; ++i) { Qi_s[i * LDU + lane - M] = cinv[i]; if (fg) fg[i * M + lane - M] = cinv[i]; }
+        }
+      }
+      __syncwarp();
+      // ---- K = -Quu^-1 Qux, k = -Quu^-1 qu
+      {
+        double Kt[4][2];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { Kt[c][0] = 0.0; Kt[c][1] = 0.0; }
+#pragma unroll
+        for (int k0 = 0; k0 < M; k0 += 4) {
+          const double a = Qi_s[gr * LDU + k0 + tg];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dmma(Kt[c], a, Qux_s[(k0 + tg) * LDQ + c * 8 + gr]);
+        }
+        const double2 qi2 = *reinterpret_cast<const double2*>(Qi_s + gr * LDU + 2 * tg);
+        const double2 qu2 = *reinterpret_cast<const double2*>(qu_s + 2 * tg);
+        const double kk = -quad_sum(__fma_rn(qi2.x, qu2.x, qi2.y * qu2.y));
+        if (tg == 0) { kk_s[gr] = kk; p.ks[idx * M + gr] = kk; }
+        __syncwarp();                                  // every lane has read the Qux panel: K may overwrite it
+        double* Kg = p.Ks + idx * (M * N) + gr * N + 2 * tg;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double2 k2 = make_double2(-Kt[c][0], -Kt[c][1]);
+          *reinterpret_cast<double2*>(K_s + gr * LDK + c * 8 + 2 * tg) = k2;
+          *reinterpret_cast<double2*>(Kg + c * 8) = k2;
+        }
+      }
+      if (fg) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          *reinterpret_cast<double2*>(fg + M * M + (r * 8 + gr) * M + 2 * tg) = make_double2(Qxu[r][0], Qxu[r][1]);
+      }
+      __syncwarp();
+      // ---- V = Qxx + Qxu K, v = qx + Qxu k.  The reference's extra terms K^T (Qux + Quu K) and K^T (qu + Quu k)
+      //      (lqr_recursion.py:151-152) vanish identically for the exact gain.
+      if (t > 0) {
+        const double2 kp = *reinterpret_cast<const double2*>(kk_s + 2 * tg);
+#pragma unroll
+        for (int ee = 0; ee < 2; ++ee)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double b = K_s[(2 * tg + ee) * LDK + c * 8 + gr];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dmma(Qxx[r][c], Qxu[r][ee], b);
+          }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          vr[r] = qx[r] + quad_sum(__fma_rn(Qxu[r][0], kp.x, Qxu[r][1] * kp.y));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { Vr[r][c][0] = Qxx[r][c][0]; Vr[r][c][1] = Qxx[r][c][1]; }
+        }
+      }
+    }
+  }
+
+  // ---- rollout (lqr_recursion.py:160-200): the warp re-streams K_t, k_t, F_t, f_t through two stages; an L2 bulk
+  //      prefetch four steps ahead keeps the (short) steps from waiting on DRAM
+  if (p.flags & LQR_DO_ROLLOUT) {
+    constexpr int LDKR = Cfg::LDKR, PD = 4;
+    __threadfence_block();
+    __syncwarp();                                  // K_t, k_t written above by other lanes of this warp
+    double* xs = sm + Cfg::Oxs;                    // [x; u]
+    double* xn = sm + Cfg::Oxn;
+    auto load_roll = [&](int t, int st) {
+      double* base = sm + st * Cfg::RSTG;
+      const size_t idx = (size_t)t * tb + e;
+      const double* Kg = p.Ks + idx * (M * N);
+#pragma unroll
+      for (int it = 0; it < M * N / 64; ++it) {    // 128 chunks, 16 per row of K
+        const int q = it * 32 + lane, row = q >> 4, cc = q & 15;
+        cp_async16(base + Cfg::RK + row * LDKR + cc * 2, Kg + q * 2);
+      }
+      if (lane < M / 2) cp_async16(base + Cfg::Rk + lane * 2, p.ks + idx * M + lane * 2);
+      if (t < T - 1) {
+        stage_F(base + Cfg::RF, p.F + idx * (N * S), lane);
+        if (have_f && lane < N / 2) cp_async16(base + Cfg::Rf + lane * 2, p.f + idx * N + lane * 2);
+      }
+      cp_async_commit();
+    };
+    if (lane < PD && lane + 1 < T - 1) l2_prefetch_bulk(p.F + ((size_t)(lane + 1) * tb + e) * (N * S), N * S * 8);
+    load_roll(0, 0);
+    xs[lane] = p.x0[(size_t)e * N + lane];
+    int st = 0;
+    for (int t = 0; t < T; ++t) {
+      cp_async_wait<0>();
+      __syncwarp();
+      if (t + 1 < T) load_roll(t + 1, st ^ 1);
+      if (lane == 0 && t + 1 + PD < T - 1) l2_prefetch_bulk(p.F + ((size_t)(t + 1 + PD) * tb + e) * (N * S), N * S * 8);
+      const double* Fs = sm + st * Cfg::RSTG + Cfg::RF;
+      const double* fs = sm + st * Cfg::RSTG + Cfg::Rf;
+      const double* Kt = sm + st * Cfg::RSTG + Cfg::RK;
+      const double* kt = sm + st * Cfg::RSTG + Cfg::Rk;
+      {   // u = K x + k : control g, interleaved quarter of the states per lane (bank-conflict free with LDKR = 36)
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) a = __fma_rn(Kt[gr * LDKR + 4 * i + tg], xs[4 * i + tg], a);
+        a = quad_sum(a);
+        if (tg == 0) xs[N + gr] = a + kt[gr];
+      }
+      __syncwarp();
+      const size_t idx = (size_t)t * tb + e;
+      if (p.x) p.x[idx * N + lane] = xs[lane];
+      if (p.u && lane < M) p.u[idx * M + lane] = xs[N + lane];
+      if (p.tau_out) { p.tau_out[idx * S + lane] = xs[lane]; if (lane < M) p.tau_out[idx * S + N + lane] = xs[N + lane]; }
+      if (t < T - 1) {   // x' = F [x; u] + f : one state per lane, four accumulation chains
+        double a0 = have_f ? fs[lane] : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int j = 0; j < S; j += 4) {
+          a0 = __fma_rn(Fs[lane * LDF + j], xs[j], a0);
+          a1 = __fma_rn(Fs[lane * LDF + j + 1], xs[j + 1], a1);
+          a2 = __fma_rn(Fs[lane * LDF + j + 2], xs[j + 2], a2);
+          a3 = __fma_rn(Fs[lane * LDF + j + 3], xs[j + 3], a3);
+        }
+        xn[lane] = (a0 + a1) + (a2 + a3);
+        __syncwarp();
+        xs[lane] = xn[lane];
+      }
+      st ^= 1;
+    }
+  }
+}
+
+}  // namespace dmpc

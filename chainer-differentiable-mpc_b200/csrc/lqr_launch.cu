@@ -3,6 +3,7 @@
 #include <type_traits>
 #include "launch.h"
 #include "lqr_dmma.cuh"
+#include "lqr_dmma_warp.cuh"
 
 #ifndef DMPC_REAL
 #define DMPC_REAL double
@@ -48,8 +49,24 @@ static bool dmma_enabled() {
   return v == 1;
 }
 
-// n=32, m=8, fp64: Riccati sweep on DMMA (lqr_dmma.cuh) + a compact rollout launch
+static bool dmma_cta_kernel() {        // DMPC_DMMA_CTA=1: first-generation CTA-per-element kernel (A/B runs)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DMPC_DMMA_CTA"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+// n=32, m=8, fp64: Riccati sweep on DMMA.  Default = warp-per-element register-resident kernel
+// (lqr_dmma_warp.cuh, rollout fused in); rollout-only calls use a compact launch of the generic kernel.
 static int launch_lqr_solve_dmma(const LqrParams<double>& p, cudaStream_t st, long long* nl) {
+  if ((p.flags & LQR_DO_FACTOR) && !dmma_cta_kernel()) {
+    constexpr int WPC = 4;
+    const size_t smem = (size_t)WPC * WarpCfg::TOTAL * sizeof(double);
+    auto kern = lqr_factor_dmma_warp_kernel<WPC>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DMPC_ERR_CUDA;
+    kern<<<(p.B + WPC - 1) / WPC, WPC * 32, smem, st>>>(p);
+    if (nl) ++*nl;
+    return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+  }
   if (p.flags & LQR_DO_FACTOR) {
     using Cfg = DmmaCfg<32, 8>;
     const size_t smem = (size_t)Cfg::TOTAL * sizeof(double);
