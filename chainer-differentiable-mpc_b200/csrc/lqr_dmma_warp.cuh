@@ -42,6 +42,35 @@ __device__ __forceinline__ double quad_sum(double a) {      // sum over the 4 la
   return a;
 }
 
+// One pivot step of the Gauss-Jordan inverse (see warp_gj_inverse in lqr_dmma.cuh), branch-free so that the
+// compiler can interleave it with the independent DMMA stream of the Q passes.
+template <int M>
+__device__ __forceinline__ void gj_step(double (&c)[M], const int k) {
+  constexpr unsigned FULL = 0xffffffffu;
+  double pc[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) pc[i] = __shfl_sync(FULL, c[i], k);
+  int piv = k;
+  unsigned best = abs_hi(pc[k]);
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+    if (i > k) { const unsigned a = abs_hi(pc[i]); const bool g = a > best; best = g ? a : best; piv = g ? i : piv; }
+  double ck = c[k], pk = pc[k];
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+    if (i > k) {
+      const bool sw = (piv == i);
+      ck = sw ? c[i] : ck; pk = sw ? pc[i] : pk;
+      c[i] = sw ? c[k] : c[i]; pc[i] = sw ? pc[k] : pc[i];
+    }
+  const double rp = fast_rcp(pk);
+  ck *= rp;
+  c[k] = ck;
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+    if (i != k) c[i] = __fma_rn(-pc[i], ck, c[i]);
+}
+
 struct WarpCfg {
   static constexpr int N = 32, M = 8, S = 40;
   // F buffer: row pitch 42 doubles -> the four fragment rows 2t+e of a half-warp fall in distinct 32-byte
@@ -52,14 +81,15 @@ struct WarpCfg {
   static constexpr int LDQ = 36;     // Qux panel [8][36]: B fragments by rows k0+t
   static constexpr int LDU = 12;     // Quu / Quu^-1 [8][12]: A fragments by rows g
   static constexpr int LDK = 34;     // K panel [8][34]: B fragments by rows 2t+e (aliases the Qux panel)
-  static constexpr int OQux = OSCR, OK = OQux, OQuu = OQux + M * LDQ, OQi = OQuu + M * LDU, Omv = OQi,
-                       Oqu = OQi + M * LDU, Okk = Oqu + M, TOTAL = Okk + M;
+  static constexpr int OQux = OSCR, OK = OQux, OQuu = OQux + M * LDQ, OQi = OQuu + M * LDU, Oqu = OQi + M * LDU,
+                       Okk = Oqu + M, Omv = Okk + M, Obar = Omv + N, TOTAL = Obar + 2;   // two mbarriers per warp
   // rollout: two stages {F, f, K_t [8][36], k_t} carved from the same region, then x|u and x_next
   static constexpr int LDKR = 36;
   static constexpr int RF = 0, Rf = RF + N * LDF, RK = Rf + N, Rk = RK + M * LDKR, RSTG = Rk + M;
   static constexpr int Oxs = 2 * RSTG, Oxn = Oxs + S;
   static_assert(Oxn + N <= TOTAL, "rollout buffers must fit");
-  static_assert(M * LDK <= M * LDQ && N <= M * LDU, "aliases must fit");
+  static_assert(M * LDK <= M * LDQ, "aliases must fit");
+  static_assert(2 * (4 * TOTAL * 8 + 1024) <= 228 * 1024, "two 4-warp CTAs per SM");
   static_assert(Of % 2 == 0 && Oc % 2 == 0 && OC % 2 == 0 && OSCR % 2 == 0 && OQuu % 2 == 0 && OQi % 2 == 0 &&
                 Oqu % 2 == 0 && Okk % 2 == 0 && RSTG % 2 == 0 && Rf % 2 == 0 && RK % 2 == 0 && Rk % 2 == 0, "16-byte alignment");
 };
@@ -68,20 +98,40 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* g, unsigned bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(g), "r"(bytes) : "memory");
 }
 
-// F_t ([32][40] contiguous in global memory) -> padded rows in shared memory, 20 x 16-byte chunks per lane.
-// Chunk q = 32 it + lane lies in row q / 20: with lane = 20 rl + cl that is a_it + rl + (cl >= 20 - b_it) for
-// the compile-time split 32 it = 20 a_it + b_it - no division and nothing to keep in registers.
-__device__ __forceinline__ void stage_F(double* Fs, const double* Fg, int lane) {
-  constexpr int LDF = WarpCfg::LDF;
-  const int rl = lane >= 20 ? 1 : 0, cl = lane - 20 * rl;
+// ---- bulk asynchronous copies (async proxy, completion on an mbarrier): one instruction moves a whole row /
+//      row block, so staging costs neither address registers nor issue slots
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DMPC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DMPC_DONE;\n"
+      "bra DMPC_WAIT;\n"
+      "DMPC_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// F_t ([32][40] contiguous in global memory) -> padded rows in shared memory: one row per cp.async instruction
+// (20 lanes x 16 bytes), so every address is base + compile-time immediate
+__device__ __forceinline__ void stage_F_rows(double* Fs, const double* Fg, int lane) {
+  if (lane < WarpCfg::S / 2) {
 #pragma unroll
-  for (int it = 0; it < 20; ++it) {
-    const int a = (32 * it) / 20, b = (32 * it) % 20;
-    const int row = a + rl + ((cl >= 20 - b) ? 1 : 0);
-    const int q = 32 * it + lane;
-    cp_async16(Fs + q * 2 + row * (LDF - 40), Fg + q * 2);
+    for (int r = 0; r < WarpCfg::N; ++r) cp_async16(Fs + r * WarpCfg::LDF + lane * 2, Fg + r * WarpCfg::S + lane * 2);
   }
 }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
 template <int WPC>
 __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel(LqrParams<double> p) {
@@ -98,46 +148,60 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
   const bool have_f = p.f != nullptr;
   const bool save_fac = (p.flags & LQR_SAVE_FAC) && p.fac;
 
+  // two mbarriers per warp (Riccati: {F,f,c} and C; rollout: one per stage); every phase opened below is waited for
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + Cfg::Obar);
+  if (lane == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncwarp();
+  unsigned par0 = 0, par1 = 0;
+
   if (p.flags & LQR_DO_FACTOR) {
     double* Fs = sm + Cfg::OF; double* fs = sm + Cfg::Of; double* cs = sm + Cfg::Oc; double* Cs = sm + Cfg::OC;
     double* Qux_s = sm + Cfg::OQux; double* Quu_s = sm + Cfg::OQuu; double* Qi_s = sm + Cfg::OQi;
     double* K_s = sm + Cfg::OK; double* qu_s = sm + Cfg::Oqu; double* kk_s = sm + Cfg::Okk; double* mv_s = sm + Cfg::Omv;
 
-    // Single-buffered, refilled just in time: a row block of C_{t-1} is requested as soon as pass i of step t has
-    // read its accumulators (a full step ahead of its use); F_{t-1}, f_{t-1}, c_{t-1} are requested after the last
-    // Q pass and land behind the gain computation - from L2, where a bulk prefetch issued one step earlier put them.
-    auto stage_C_rows = [&](int t, int i) {
-      const double* Cg = p.C + ((size_t)t * tb + e) * (S * S) + i * 8 * S;
-#pragma unroll
-      for (int it = 0; it < 8 * S / 64; ++it) cp_async16(Cs + i * 8 * S + (it * 32 + lane) * 2, Cg + (it * 32 + lane) * 2);
+    // Single-buffered, refilled just in time by bulk copies: a row block of C_{t-1} is requested as soon as pass i
+    // of step t has read its accumulators (a full step ahead of its use); F_{t-1} (one padded row per lane),
+    // f_{t-1}, c_{t-1} are requested after the last Q pass and land behind the gain computation - from L2, where
+    // a bulk prefetch issued one step earlier put them.
+    unsigned long long* barF = bars;
+    unsigned long long* barC = bars + 1;
+    auto stage_C_rows = [&](int t, int i) {            // lane 0 only
+      bulk_g2s(Cs + i * 8 * S, p.C + ((size_t)t * tb + e) * (S * S) + i * 8 * S, 8 * S * 8, barC);
     };
-    auto stage_Ffc = [&](int t) {
+    auto stage_Ffc = [&](int t) {                      // all lanes; t < T-1
       const size_t idx = (size_t)t * tb + e;
-      if (t < T - 1) {
-        stage_F(Fs, p.F + idx * (N * S), lane);
-        if (have_f && lane < N / 2) cp_async16(fs + lane * 2, p.f + idx * N + lane * 2);
+      stage_F_rows(Fs, p.F + idx * (N * S), lane);
+      cp_async_commit();
+      if (lane == 0) {
+        mbar_arrive_expect_tx(barF, (have_f ? N * 8 : 0) + S * 8);
+        bulk_g2s(cs, p.c + idx * S, S * 8, barF);
+        if (have_f) bulk_g2s(fs, p.f + idx * N, N * 8, barF);
       }
-      if (lane < S / 2) cp_async16(cs + lane * 2, p.c + idx * S + lane * 2);
     };
 
     // V_t as accumulator-layout registers: Vr[r][kb][e] = V[8r+g][8kb+2t+e];  vr[r] = v[8r+g]
+    // v_t and q_x live in shared memory between their producer and consumer (v aliases mv, q_x aliases Quu)
     double Vr[4][4][2];
-    double vr[4];
+    double* v_s = mv_s; double* qx_s = Quu_s;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      vr[r] = 0.0;
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) { Vr[r][kb][0] = 0.0; Vr[r][kb][1] = 0.0; }
     }
 
-#pragma unroll
-    for (int i = 0; i < 5; ++i) stage_C_rows(T - 1, i);
-    stage_Ffc(T - 1);
-    cp_async_commit();
+    if (lane == 0) {                                   // step T-1 needs C and c only
+      mbar_arrive_expect_tx(barC, S * S * 8);
+      bulk_g2s(Cs, p.C + ((size_t)(T - 1) * tb + e) * (S * S), S * S * 8, barC);
+      mbar_arrive_expect_tx(barF, S * 8);
+      bulk_g2s(cs, p.c + ((size_t)(T - 1) * tb + e) * S, S * 8, barF);
+    }
     if (T > 1 && lane == 0) l2_prefetch_bulk(p.F + ((size_t)(T - 2) * tb + e) * (N * S), N * S * 8);
 
     for (int t = T - 1; t >= 0; --t) {
       cp_async_wait<0>();
+      mbar_wait(barF, par0); par0 ^= 1;
+      mbar_wait(barC, par1); par1 ^= 1;
       __syncwarp();                                    // C_t, F_t, f_t, c_t are resident
       if (t > 1 && lane == 0) l2_prefetch_bulk(p.F + ((size_t)(t - 2) * tb + e) * (N * S), N * S * 8);
       const size_t idx = (size_t)t * tb + e;
@@ -159,8 +223,9 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
             }
             a = quad_sum(a);
           }
-          mvr[r] = a + vr[r];
+          mvr[r] = a + v_s[r * 8 + gr];
         }
+        __syncwarp();                                  // every lane has read v before mv overwrites it
         if (tg == 0) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) mv_s[r * 8 + gr] = mvr[r];
@@ -186,8 +251,11 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
         __syncwarp();                                  // mv_s complete
       }
 
-      // ---- Q = C + F^T W (row block u first), q = c + F^T mv
-      double Qxx[4][4][2], Qxu[4][2], qx[4];
+      // ---- Q = C + F^T W (row block u first), q = c + F^T mv.  The Gauss-Jordan inverse of Quu (available after
+      //      the first pass) is interleaved with the DMMAs of the next two passes: 8 pivot steps, one per two k-steps.
+      double Qxx[4][4][2], Qxu[4][2];
+      double cinv[M];
+      double* fg = save_fac ? p.fac + idx * (M * M + N * M) : nullptr;
 #pragma unroll
       for (int pi = 0; pi < 5; ++pi) {
         const int i = (pi == 0) ? 4 : pi - 1;
@@ -198,7 +266,14 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
           acc[j][0] = c2.x; acc[j][1] = c2.y;
         }
         __syncwarp();
-        if (t > 0) stage_C_rows(t - 1, i);             // refill this row block for the next step
+        if (t > 0 && lane == 0) {                      // refill this row block for the next step
+          if (pi == 0) mbar_arrive_expect_tx(barC, S * S * 8);
+          stage_C_rows(t - 1, i);
+        }
+        if (pi == 1) {
+#pragma unroll
+          for (int ii = 0; ii < M; ++ii) cinv[ii] = (lane < M) ? Quu_s[ii * LDU + lane] : ((lane - M == ii) ? 1.0 : 0.0);
+        }
         double qa = 0.0;
         if (!last) {
 #pragma unroll
@@ -210,9 +285,13 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
 #pragma unroll
               for (int j = 0; j < 5; ++j) dmma(acc[j], a, WT[j][r][ee]);
               qa = __fma_rn(a, ee ? m2.y : m2.x, qa);
+              if ((pi == 1 || pi == 2) && ee == 1) gj_step<M>(cinv, (pi - 1) * 4 + r);
             }
           }
           qa = quad_sum(qa);
+        } else if (pi == 1 || pi == 2) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) gj_step<M>(cinv, (pi - 1) * 4 + r);
         }
         qa += cs[i * 8 + gr];
         if (i == 4) {
@@ -225,24 +304,15 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
 #pragma unroll
           for (int j = 0; j < 4; ++j) { Qxx[i][j][0] = acc[j][0]; Qxx[i][j][1] = acc[j][1]; }
           Qxu[i][0] = acc[4][0]; Qxu[i][1] = acc[4][1];
-          qx[i] = qa;
+          if (tg == 0) qx_s[i * 8 + gr] = qa;
+        }
+        if (pi == 2 && lane >= M && lane < 2 * M) {    // lanes 8..15 hold the columns of Quu^-1
+#pragma unroll
+          for (int ii = 0; ii < M; ++ii) { Qi_s[ii * LDU + lane - M] = cinv[ii]; if (fg) fg[ii * M + lane - M] = cinv[ii]; }
         }
       }
-      __syncwarp();                                    // F_t, f_t, c_t, mv are dead; Qux, Quu, qu are complete
-      if (t > 0) { stage_Ffc(t - 1); cp_async_commit(); }
-
-      // ---- Quu^-1 (Gauss-Jordan, partial pivoting; lanes 8..15 end up with its columns)
-      double* fg = save_fac ? p.fac + idx * (M * M + N * M) : nullptr;
-      {
-        double cinv[M];
-#pragma unroll
-        for (int i = 0; i < M; ++i) cinv[i] = (lane < M) ? Quu_s[i * LDU + lane] : ((lane - M == i) ? 1.0 : 0.0);
-        warp_gj_inverse<M>(cinv);
-        if (lane >= M && lane < 2 * M) {               // (Qi aliases mv, dead since the barrier above)
-#pragma unroll
-          for (int i = 0; i < M; ++i) { Qi_s[i * LDU + lane - M] = cinv[i]; if (fg) fg[i * M + lane - M] = cinv[i]; }
-        }
-      }
+      __syncwarp();                                    // F_t, f_t, c_t, mv are dead; Qux, Quu^-1, qu are complete
+      if (t > 0) stage_Ffc(t - 1);
       __syncwarp();
       // ---- K = -Quu^-1 Qux, k = -Quu^-1 qu
       {
@@ -288,7 +358,8 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
           }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          vr[r] = qx[r] + quad_sum(__fma_rn(Qxu[r][0], kp.x, Qxu[r][1] * kp.y));
+          const double vn = qx_s[r * 8 + gr] + quad_sum(__fma_rn(Qxu[r][0], kp.x, Qxu[r][1] * kp.y));
+          if (tg == 0) v_s[r * 8 + gr] = vn;
 #pragma unroll
           for (int c = 0; c < 4; ++c) { Vr[r][c][0] = Qxx[r][c][0]; Vr[r][c][1] = Qxx[r][c][1]; }
         }
@@ -304,9 +375,12 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
     __syncwarp();                                  // K_t, k_t written above by other lanes of this warp
     double* xs = sm + Cfg::Oxs;                    // [x; u]
     double* xn = sm + Cfg::Oxn;
+    __syncwarp();
     auto load_roll = [&](int t, int st) {
       double* base = sm + st * Cfg::RSTG;
       const size_t idx = (size_t)t * tb + e;
+      const bool hasF = t < T - 1;
+      if (hasF) stage_F_rows(base + Cfg::RF, p.F + idx * (N * S), lane);
       const double* Kg = p.Ks + idx * (M * N);
 #pragma unroll
       for (int it = 0; it < M * N / 64; ++it) {    // 128 chunks, 16 per row of K
@@ -314,13 +388,11 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
         cp_async16(base + Cfg::RK + row * LDKR + cc * 2, Kg + q * 2);
       }
       if (lane < M / 2) cp_async16(base + Cfg::Rk + lane * 2, p.ks + idx * M + lane * 2);
-      if (t < T - 1) {
-        stage_F(base + Cfg::RF, p.F + idx * (N * S), lane);
-        if (have_f && lane < N / 2) cp_async16(base + Cfg::Rf + lane * 2, p.f + idx * N + lane * 2);
-      }
+      if (hasF && have_f && lane >= 16) cp_async16(base + Cfg::Rf + (lane - 16) * 2, p.f + idx * N + (lane - 16) * 2);
       cp_async_commit();
     };
     if (lane < PD && lane + 1 < T - 1) l2_prefetch_bulk(p.F + ((size_t)(lane + 1) * tb + e) * (N * S), N * S * 8);
+    if (lane >= 8 && lane < 8 + PD && lane - 7 < T) l2_prefetch_bulk(p.Ks + ((size_t)(lane - 7) * tb + e) * (M * N), M * N * 8);
     load_roll(0, 0);
     xs[lane] = p.x0[(size_t)e * N + lane];
     int st = 0;
@@ -329,6 +401,7 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
       __syncwarp();
       if (t + 1 < T) load_roll(t + 1, st ^ 1);
       if (lane == 0 && t + 1 + PD < T - 1) l2_prefetch_bulk(p.F + ((size_t)(t + 1 + PD) * tb + e) * (N * S), N * S * 8);
+      if (lane == 1 && t + 1 + PD < T) l2_prefetch_bulk(p.Ks + ((size_t)(t + 1 + PD) * tb + e) * (M * N), M * N * 8);
       const double* Fs = sm + st * Cfg::RSTG + Cfg::RF;
       const double* fs = sm + st * Cfg::RSTG + Cfg::Rf;
       const double* Kt = sm + st * Cfg::RSTG + Cfg::RK;
