@@ -54,6 +54,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """Measured DRAM bytes per solve of each kernel (one ncu --set full capture each, committed under profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r1", "traffic.json")
+    try:
+        with open(path) as fh:
+            return {k: v for k, v in json.load(fh).items() if not k.startswith("_")}
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -235,17 +245,20 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    # ---- kernel-level durations (serial, chunk 0, events on the launching stream) for the roofline
-    kt = {"factor": [], "rollout": [], "adjoint": []}
+    # ---- kernel-level durations (serial, chunk 0, events on the launching stream) for the roofline.
+    #      "forward" is the launch the timed step really makes (Riccati sweep + rollout fused); the factor-only
+    #      and rollout-only launches are timed beside it to split it; "adjoint" = lqr_dtau_kernel + adjoint_out_kernel.
+    kt = {"forward": [], "factor": [], "rollout": [], "adjoint": []}
     for _ in range(3):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         e[0].record(sA)
-        fwd(0, sA, _native.LQR_FACTOR | _native.LQR_SAVE_FAC); e[1].record(sA)
-        fwd(0, sA, _native.LQR_ROLLOUT); e[2].record(sA)
-        bwd(0, sA); e[3].record(sA)
+        fwd(0, sA, FULL); e[1].record(sA)
+        bwd(0, sA); e[2].record(sA)
+        fwd(0, sA, _native.LQR_FACTOR | _native.LQR_SAVE_FAC); e[3].record(sA)
+        fwd(0, sA, _native.LQR_ROLLOUT); e[4].record(sA)
         torch.cuda.synchronize()
-        kt["factor"].append(e[0].elapsed_time(e[1])); kt["rollout"].append(e[1].elapsed_time(e[2]))
-        kt["adjoint"].append(e[2].elapsed_time(e[3]))
+        kt["forward"].append(e[0].elapsed_time(e[1])); kt["adjoint"].append(e[1].elapsed_time(e[2]))
+        kt["factor"].append(e[2].elapsed_time(e[3])); kt["rollout"].append(e[3].elapsed_time(e[4]))
     kt = {k: float(np.mean(v)) for k, v in kt.items()}
     # ---- timed region
     sampler = ClockSampler(local)
@@ -273,25 +286,42 @@ def run_b200(args):
     if rank == 0:
         fwd_b, tot_b = algorithmic_bytes(n, m, T)
         peak, peak_src = measured_peaks()
-        # dominant kernel = the Riccati sweep; its algorithmic bytes are the forward reads (C,c,F,f,x0)
-        fac_b = fwd_b - 8 * T * s
-        dom = max(kt, key=kt.get)
-        dom_bytes = {"factor": fac_b, "rollout": 8 * ((T - 1) * (n * s + n) + T * (m * n + m) + T * s + n),
-                     "adjoint": tot_b - fwd_b}[dom]
-        dom_name = {"factor": "lqr_factor_dmma_kernel" if (n, m) == (32, 8) else "lqr_solve_kernel(FACTOR)",
-                    "rollout": "lqr_solve_kernel(ROLLOUT)", "adjoint": "lqr_dtau_kernel+adjoint_out_kernel"}[dom]
-        achieved = Bc * dom_bytes / (kt[dom] * 1e-3) / 1e9
+        traffic = ncu_traffic()
+        dmma = (n, m) == (32, 8)
+        fwd_name = "lqr_factor_dmma_warp_kernel" if dmma else "lqr_solve_kernel"
+        kernels = {
+            fwd_name: {"ms": kt["forward"], "launches_per_step": 1, "algorithmic_bytes": Bc * fwd_b,
+                       "role": "Riccati sweep + rollout, one launch (factor-only %.3f ms, rollout-only %.3f ms)" % (kt["factor"], kt["rollout"])},
+            "lqr_dtau_kernel+adjoint_out_kernel": {"ms": kt["adjoint"], "launches_per_step": 2,
+                                                   "algorithmic_bytes": Bc * (tot_b - fwd_b), "role": "KKT adjoint"}}
+        for name, k in kernels.items():
+            k["achieved_gbs"] = k["algorithmic_bytes"] / (k["ms"] * 1e-3) / 1e9
+            k["hbm_frac"] = k["achieved_gbs"] / peak
+            tb = [traffic[x]["bytes_per_solve"] for x in name.split("+") if x in traffic] if dmma else []
+            k["traffic"] = Bc * sum(tb) if tb and len(tb) == len(name.split("+")) else None
+            if k["traffic"]:
+                k["traffic_gbs"] = k["traffic"] / (k["ms"] * 1e-3) / 1e9
+        dom = max(kernels, key=lambda x: kernels[x]["ms"])
         whole = B * tot_b / (ms_step * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel_ms_per_chunk": kt, "chunk_batch": Bc,
-                "whole_step_achieved": whole, "whole_step_frac": whole / peak,
-                "algorithmic_bytes_per_solve": {"fwd": fwd_b, "fwd_bwd": tot_b}}
-        if (n, m) == (32, 8):
-            flops = 400 * 512 * T          # DMMA flops of the Riccati sweep per solve
-            tf = Bc * flops / (kt["factor"] * 1e-3) / 1e12
-            roof["fp64_tensor"] = {"achieved_tflops": tf, "peak_tflops": 37.15, "frac": tf / 37.15,
-                                   "peak_source": "measured, profiles/r1/fp64_peak.json"}
+        if dmma and dom == fwd_name:
+            # the dominant launch is bound by the FP64 tensor (DMMA) pipe: 400 DMMA m8n8k4 (512 flop) per element-step
+            #  = 20.5 Mflop per solve; HBM floor of its algorithmic bytes is lower (see kernels[...])
+            flops = 400 * 512 * T
+            tf = Bc * flops / (kt["forward"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": dom, "achieved": tf, "peak": 37.15, "unit": "TFLOP/s", "frac": tf / 37.15,
+                    "traffic": kernels[dom]["traffic"],
+                    "peak_source": "FP64 DMMA m8n8k4 peak measured on this pool's B200 (profiles/tools/fp64_peak.cu -> "
+                                   "profiles/r1/fp64_peak.json); MEASURED_PEAKS.json carries no FP64 figure",
+                    "algorithmic_flops_per_launch": Bc * flops,
+                    "factor_only_frac": Bc * flops / (kt["factor"] * 1e-3) / 1e12 / 37.15}
+        else:
+            k = kernels[dom]
+            roof = {"bound": "hbm", "kernel": dom, "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": k["hbm_frac"], "traffic": k["traffic"], "peak_source": peak_src}
+        roof.update({"hbm_peak_gbs": peak, "hbm_peak_source": peak_src, "kernels": kernels, "chunk_batch": Bc,
+                     "whole_step_achieved_gbs": whole, "whole_step_hbm_frac": whole / peak,
+                     "algorithmic_bytes_per_solve": {"fwd": fwd_b, "fwd_bwd": tot_b},
+                     "traffic_source": "ncu dram__bytes_read+write per solve x launch batch (profiles/r1/traffic.json)"})
         line = {"metric": "lqr_fwd_bwd_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -528,7 +558,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
     ap.add_argument("--e2e-batch", type=int, default=512)
-    ap.add_argument("--e2e-workers", type=int, default=2)
+    ap.add_argument("--e2e-workers", type=int, default=3)
     ap.add_argument("--chunks", type=int, default=1, help="sub-batches per GPU; >1 overlaps fwd(i+1) with bwd(i)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true")

@@ -7,6 +7,8 @@ the symbol table can be checked), but creating a context raises.
 import ctypes
 import os
 
+import threading
+
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -86,6 +88,25 @@ def dtype_code(dt):
     raise DiffMpcError("unsupported dtype %s (float64 / float32 only)" % dt)
 
 
+# ---- host<->device link arbitration ---------------------------------------------------------------------
+# A forward call is upload-heavy and a backward call download-heavy.  When several host threads feed one GPU
+# (one Context each), letting each direction of the PCIe link serve ONE caller's burst at a time makes the
+# callers fall into anti-phase (A downloads while B uploads) and keeps both directions busy; interleaving
+# same-direction bursts would only stretch both.  One lock per (device, direction), process-wide.
+_LINK_LOCKS = {}
+_LINK_LOCKS_GUARD = threading.Lock()
+
+
+def link_lock(device, direction):
+    """`with link_lock(dev, "h2d"):` around a burst of uploads (or "d2h" downloads) including its stream sync."""
+    key = (int(device), direction)
+    with _LINK_LOCKS_GUARD:
+        lk = _LINK_LOCKS.get(key)
+        if lk is None:
+            lk = _LINK_LOCKS[key] = threading.Lock()
+    return lk
+
+
 class DeviceArray:
     """A typed, shaped cudaMalloc'ed buffer owned by a Context."""
 
@@ -104,12 +125,13 @@ class DeviceArray:
         # pageable memcpyAsync returns after staging, so `arr` may be released
         return self
 
-    def download(self, out=None, stream=None):
+    def download(self, out=None, stream=None, sync=True):
         if out is None:
             out = np.empty(self.shape, dtype=self.dtype)
         assert out.flags["C_CONTIGUOUS"] and out.nbytes == self.nbytes
         self.ctx._check(self.ctx.lib.dmpc_memcpy_d2h(self.ctx.h, out.ctypes.data, self.ptr, self.nbytes, stream))
-        self.ctx.sync(stream)
+        if sync:
+            self.ctx.sync(stream)
         return out
 
     def zero(self, stream=None):

@@ -71,38 +71,47 @@ class DiffLqr(FunctionNodeBase):
         assert list(C.shape) == [T, B, s, s], "C dim mismatch"
         assert list(c.shape) == [T, B, s], "c dim mismatch"
         d = self._buffers()
-        d["x0"].upload(x_init); d["C"].upload(C); d["c"].upload(c)
+        F = None
         if T > 1:
             F = as_f(large_f, dt)
             if F.shape[0] == T:
                 F = F[:T - 1]
             assert list(F.shape) == [T - 1, B, n, s], "F dim mismatch"
-            d["F"].upload(F)
         self._have_f = f is not None and to_xp(f) is not None
         if self._have_f and T > 1:
             f = as_f(f, dt)
             assert list(f.shape) == [T - 1, B, n], " f dim mismatch"
-            d["f"].upload(f)
-        self._ctx.lqr_solve(dt, T, B, n, m, d["x0"], d["C"], d["c"], d["F"], T - 1, d["f"] if self._have_f else None,
-                            d["x"], d["u"], d["Ks"], d["ks"], d["fac"],
-                            _native.LQR_FACTOR | _native.LQR_ROLLOUT | _native.LQR_SAVE_FAC)
-        x = d["x"].download(self._host_buf("x", (T, B, n)))
+        ctx = self._ctx
+        with _native.link_lock(ctx.device, "h2d"):      # one caller's upload burst at a time (see _native.link_lock)
+            d["x0"].upload(x_init); d["C"].upload(C); d["c"].upload(c)
+            if F is not None:
+                d["F"].upload(F)
+            if self._have_f and T > 1:
+                d["f"].upload(f)
+            ctx.sync()
+        ctx.lqr_solve(dt, T, B, n, m, d["x0"], d["C"], d["c"], d["F"], T - 1, d["f"] if self._have_f else None,
+                      d["x"], d["u"], d["Ks"], d["ks"], d["fac"],
+                      _native.LQR_FACTOR | _native.LQR_ROLLOUT | _native.LQR_SAVE_FAC)
+        x = d["x"].download(self._host_buf("x", (T, B, n)), sync=False)
         u = d["u"].download(self._host_buf("u", (T, B, m)))
         return x, u
 
     def backward_numpy(self, grad_x, grad_u):
         T, B, n, m, s, dt = self.T, self.n_batch, self.n_state, self.n_ctrl, self.n_sc, self.dtype
         d = self._buffers()
+        ctx = self._ctx
         d["gx"].upload(as_f(grad_x, dt)); d["gu"].upload(as_f(grad_u, dt))
-        self._ctx.lqr_adjoint(dt, T, B, n, m, d["C"], d["c"], d["F"], d["x"], d["u"], d["gx"], d["gu"], d["Ks"],
-                              d["fac"], d["dx0"], d["dC"], d["dc"], d["dF"], d["df"],
-                              _native.ADJ_STRICT_REFERENCE if self.strict_reference else 0)
-        dx0 = d["dx0"].download(self._host_buf("dx0", (B, n)))
-        dC = d["dC"].download(self._host_buf("dC", (T, B, s, s)))
-        dc = d["dc"].download(self._host_buf("dc", (T, B, s)))
+        ctx.lqr_adjoint(dt, T, B, n, m, d["C"], d["c"], d["F"], d["x"], d["u"], d["gx"], d["gu"], d["Ks"],
+                        d["fac"], d["dx0"], d["dC"], d["dc"], d["dF"], d["df"],
+                        _native.ADJ_STRICT_REFERENCE if self.strict_reference else 0)
         Tm = max(T - 1, 1)
-        dF = d["dF"].download(self._host_buf("dF", (Tm, B, n, s)))[:T - 1]
-        df = d["df"].download(self._host_buf("df", (Tm, B, n)))[:T - 1]
+        ctx.sync()                                      # kernels done: take the download lane only for the copies
+        with _native.link_lock(ctx.device, "d2h"):
+            dx0 = d["dx0"].download(self._host_buf("dx0", (B, n)), sync=False)
+            dC = d["dC"].download(self._host_buf("dC", (T, B, s, s)), sync=False)
+            dc = d["dc"].download(self._host_buf("dc", (T, B, s)), sync=False)
+            dF = d["dF"].download(self._host_buf("dF", (Tm, B, n, s)), sync=False)[:T - 1]
+            df = d["df"].download(self._host_buf("df", (Tm, B, n)))[:T - 1]
         return dx0, dC, dc, dF, df
 
     # ---- Chainer FunctionNode protocol (reference :41-142) -----------------------------------
