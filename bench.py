@@ -186,6 +186,8 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     ctx = _native.Context(local)
     f64 = torch.float64
@@ -331,6 +333,24 @@ def run_b200(args):
                            "l2": "inputs (%.1f GB/GPU) larger than L2" % (B * fwd_b / 1e9), "finite_outputs": ok},
                 "roofline": roof, "clocks": clocks, "gpu_launches": launches}
 
+    # ---- the one exchange step of a training iteration: (T,B_local)-reduce the learned-dynamics
+    #      gradient dF and all-reduce(sum) it over the ranks (NCCL); reported, not part of the solve metric
+    exch = None
+    if dist is not None:
+        _, out0 = chunks[0]
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True); ev2 = torch.cuda.Event(enable_timing=True)
+        red_ms, ar_ms = [], []
+        for _ in range(8):
+            ev0.record()
+            gF = out0["dF"].sum(dim=(0, 1))
+            ev1.record()
+            dist.all_reduce(gF, op=dist.ReduceOp.SUM)
+            ev2.record()
+            torch.cuda.synchronize()
+            red_ms.append(ev0.elapsed_time(ev1)); ar_ms.append(ev1.elapsed_time(ev2))
+        exch = {"what": "sum_(t,b) dF -> [n,s] then NCCL all_reduce(sum) of %d doubles" % (n * s),
+                "local_reduce_ms": float(np.median(red_ms)), "allreduce_ms": float(np.median(ar_ms)), "world": world}
+
     # ---- e2e through the public API with host buffers (rank-local chunk) -----------------
     e2e = None
     try:
@@ -339,6 +359,8 @@ def run_b200(args):
         e2e = {"value": None, "unit": "solves/s", "error": repr(ex)[:200]}
     if rank == 0:
         line["e2e"] = e2e
+        if exch is not None:
+            line["param_grad_exchange"] = exch
         if world == 1 and not args.no_cpu:
             Bcpu = cpu_sample_batch(n, m, T)
             cpu_lqr_fwd_bwd(n, m, T, min(Bcpu, 32))

@@ -52,7 +52,19 @@ SIGNATURES = {
     "dmpc_mpc_step_backward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i] + [_vp] * 15 + [_vp]),
     "dmpc_lqr_active_solve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dmpc_get_traj": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(_d), _vp, _vp, _vp, _vp]),
+    "dmpc_boxddp_workspace_bytes": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(_sz)]),
+    "dmpc_boxddp_solve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, ctypes.POINTER(_d), _vp,
+                               _vp, _vp, _sz] + [_vp] * 7 + [ctypes.POINTER(_i)] * 3 + [_vp]),
 }
+
+
+class BoxDdpOpts(ctypes.Structure):
+    """dmpc_boxddp_opts of include/diffmpc_b200.h."""
+    _fields_ = [("eps", _d), ("best_cost_eps", _d), ("ls_decay", _d), ("not_improved_lim", _i), ("max_iter", _i),
+                ("max_ls_trials", _i), ("coupling", _i)]
+
+
+BOXDDP_MAX_ITER, BOXDDP_CONVERGED, BOXDDP_NOT_IMPROVED = 0, 1, 2
 
 _lib = None
 
@@ -280,6 +292,26 @@ class Context:
     def get_traj(self, dtype, T, B, n, m, dynamics, x0, u, F, f, dyn_params, x, Fout=None, fout=None, stream=None):
         self._check(self.lib.dmpc_get_traj(self.h, dtype_code(dtype), T, B, n, m, dynamics, _p(x0), _p(u), _p(F), _p(f),
                                            self._dynp(dyn_params), _p(x), _p(Fout), _p(fout), stream))
+
+    def boxddp_solve(self, dtype, T, B, n, m, x_init, C, c, lower, upper, dynamics, F, F_T, f, dyn_params, u_init,
+                     eps, best_cost_eps, ls_decay, not_improved_lim, max_iter, max_ls_trials, coupling,
+                     x_best, u_best, costs_best, du_best, du_last, F_lin=None, f_lin=None, stream=None):
+        """Device-resident BoxDDP loop; returns (n_iter, status, flags)."""
+        need = _sz(0)
+        self._check(self.lib.dmpc_boxddp_workspace_bytes(dtype_code(dtype), T, B, n, m, ctypes.byref(need)))
+        ws = DeviceArray(self, (int(need.value),), np.uint8)
+        opts = BoxDdpOpts(float(eps), float(best_cost_eps), float(ls_decay), int(not_improved_lim), int(max_iter),
+                          int(max_ls_trials), int(coupling))
+        n_iter, status, flags = _i(0), _i(0), _i(0)
+        try:
+            self._check(self.lib.dmpc_boxddp_solve(
+                self.h, dtype_code(dtype), T, B, n, m, _p(x_init), _p(C), _p(c), _p(lower), _p(upper), dynamics, _p(F),
+                int(F_T), _p(f), self._dynp(dyn_params), _p(u_init), ctypes.cast(ctypes.byref(opts), _vp), _p(ws),
+                int(need.value), _p(x_best), _p(u_best), _p(costs_best), _p(du_best), _p(du_last), _p(F_lin), _p(f_lin),
+                ctypes.byref(n_iter), ctypes.byref(status), ctypes.byref(flags), stream))
+        finally:
+            ws.free()
+        return int(n_iter.value), int(status.value), int(flags.value)
 
     def lqr_fac_elems(self, T, B, n, m):
         return int(self.lib.dmpc_lqr_fac_elems(T, B, n, m))

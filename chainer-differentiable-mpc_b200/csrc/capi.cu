@@ -5,6 +5,7 @@
 #include "../../include/diffmpc_b200.h"
 #include "launch.h"
 #include "mpc_launch.h"
+#include "boxddp_kernels.cuh"
 
 struct dmpc_ctx {
   int device = 0;
@@ -168,6 +169,88 @@ static int traj_impl(dmpc_handle h, int T, int B, int n, int m, int dynamics, co
   int rc = launch_traj<R>(p, st, &h->launches);
   if (rc) h->err = "get_traj launch failed";
   return rc;
+}
+
+extern "C" int dmpc_get_traj(dmpc_handle, int, int, int, int, int, int, const void*, const void*, const void*, const void*, const double*, void*, void*, void*, void*);
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident BoxDDP outer loop (reference mpc/box_ddp.py:121-230).  Everything stays in HBM; per iteration the
+// host reads one 32-byte status record to apply the reference's (batch-global) exit tests.
+namespace {
+struct BoxWs {
+  size_t x_nom, u_a, u_b, x_new, Ks, ks, u_first, objs, costs, old, alphas, du, n_qp, free_m, n_ls, flags, status, total;
+};
+inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+inline BoxWs box_ws(size_t w, int T, int B, int n, int m) {
+  BoxWs L; size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o = al256(o + bytes); return at; };
+  L.x_nom = take(w * T * B * n); L.u_a = take(w * T * B * m); L.u_b = take(w * T * B * m); L.x_new = take(w * T * B * n);
+  L.Ks = take(w * T * B * m * n); L.ks = take(w * T * B * m); L.u_first = take(w * T * B * m); L.objs = take(w * T * B);
+  L.costs = take(w * B); L.old = take(w * B); L.alphas = take(w * B); L.du = take(w * B);
+  L.n_qp = take(sizeof(int) * (size_t)T * B); L.free_m = take((size_t)T * B * m); L.n_ls = take(sizeof(int) * (size_t)B);
+  L.flags = take(sizeof(int) * (size_t)B); L.status = take(sizeof(BoxDdpStatus));
+  L.total = o;
+  return L;
+}
+}  // namespace
+
+template <typename R>
+static int boxddp_impl(dmpc_handle h, int dtype, int T, int B, int n, int m, const void* x_init, const void* C, const void* c,
+                       const void* lo, const void* hi, int dynamics, const void* F, int F_T, const void* f,
+                       const double* dynp, const void* u_init, const dmpc_boxddp_opts* o, void* ws, void* x_best,
+                       void* u_best, void* costs_best, void* du_best, void* du_last, void* F_lin, void* f_lin,
+                       int* h_n_iter, int* h_status, int* h_flags, cudaStream_t st) {
+  const BoxWs L = box_ws(sizeof(R), T, B, n, m);
+  char* w = (char*)ws;
+  R* x_nom = (R*)(w + L.x_nom); R* u_cur = (R*)(w + L.u_a); R* u_new = (R*)(w + L.u_b); R* x_new = (R*)(w + L.x_new);
+  R* Ks = (R*)(w + L.Ks); R* ks = (R*)(w + L.ks); R* u_first = (R*)(w + L.u_first); R* objs = (R*)(w + L.objs);
+  R* costs = (R*)(w + L.costs); R* old = (R*)(w + L.old); R* alphas = (R*)(w + L.alphas); R* du = (R*)(w + L.du);
+  int* n_qp = (int*)(w + L.n_qp); unsigned char* free_m = (unsigned char*)(w + L.free_m); int* n_ls = (int*)(w + L.n_ls);
+  int* flags = (int*)(w + L.flags); BoxDdpStatus* dst = (BoxDdpStatus*)(w + L.status);
+  const bool pend = dynamics == DMPC_DYN_PENDULUM;
+  const size_t ub = sizeof(R) * (size_t)T * B * m;
+  CK(cudaMemcpyAsync(u_cur, u_init, ub, cudaMemcpyDeviceToDevice, st));
+  int n_not_improved = 0, status = DMPC_BOXDDP_MAX_ITER, n_iter = 0, flags_or = 0;
+  const int tpb = 128, grid = (B + tpb - 1) / tpb;
+  for (int i = 0; i < o->max_iter; ++i) {
+    n_iter = i + 1;
+    CK(cudaMemsetAsync(dst, 0, sizeof(BoxDdpStatus), st));
+    int rc = dmpc_get_traj(h, dtype, T, B, n, m, dynamics, x_init, u_cur, F, f, dynp, x_nom, pend ? F_lin : nullptr,
+                           pend ? f_lin : nullptr, st);
+    if (rc) return rc;
+    rc = dmpc_mpc_step_forward(h, dtype, T, B, n, m, C, c, pend ? F_lin : F, pend ? T - 1 : F_T, nullptr, x_nom, u_cur, lo, hi,
+                               C, c, dynamics, pend ? nullptr : F, pend ? nullptr : f, dynp, o->ls_decay, o->max_ls_trials,
+                               1, o->coupling, x_new, u_new, Ks, ks, u_first, objs, costs, old, alphas, n_qp, free_m, n_ls,
+                               flags, st);
+    if (rc) return rc;
+    scrambled_norm_kernel<R><<<grid, tpb, 0, st>>>(T, B, m, u_cur, u_first, du);
+    best_update_kernel<R><<<grid, tpb, 0, st>>>(T, B, n, m, i == 0, (R)o->best_cost_eps, x_new, u_new, costs, du, flags,
+                                                (R*)x_best, (R*)u_best, (R*)costs_best, (R*)du_best, dst);
+    h->launches += 2;
+    BoxDdpStatus hs;
+    CK(cudaMemcpyAsync(&hs, dst, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    R* t_ = u_cur; u_cur = u_new; u_new = t_;                       // next nominal controls = this step's controls
+    flags_or |= hs.flags_or;
+    if (hs.nonfinite) { if (h_n_iter) *h_n_iter = n_iter; return fail(h, DMPC_ERR_NONFINITE, "boxddp: non-finite trajectory, cost or step norm"); }
+    n_not_improved += 1;
+    if (i > 0 && hs.any_better) n_not_improved = 0;
+    double max_du;
+    memcpy(&max_du, &hs.max_du_bits, sizeof(double));
+    if (max_du < o->eps) { status = DMPC_BOXDDP_CONVERGED; break; }       // box_ddp.py:223-225
+    if (n_not_improved > o->not_improved_lim) { status = DMPC_BOXDDP_NOT_IMPROVED; break; }   // :227-229
+  }
+  if (du_last) CK(cudaMemcpyAsync(du_last, du, sizeof(R) * (size_t)B, cudaMemcpyDeviceToDevice, st));
+  if (pend) {   // linearise at the returned point (box_ddp.py:235-242); the rollout itself is scratch
+    int rc = dmpc_get_traj(h, dtype, T, B, n, m, dynamics, x_best, u_best, nullptr, nullptr, dynp, x_nom, F_lin, f_lin, st);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(st));
+  if (h_n_iter) *h_n_iter = n_iter;
+  if (h_status) *h_status = status;
+  if (h_flags) *h_flags = flags_or;
+  return DMPC_OK;
 }
 
 extern "C" {
@@ -382,6 +465,37 @@ int dmpc_get_traj(dmpc_handle h, int dtype, int T, int B, int n, int m, int dyna
   if (dtype == DMPC_F64) return traj_impl<double>(h, T, B, n, m, dynamics, d_x0, d_u, d_F, d_f, h_dyn_params, d_x, d_Fout, d_fout, st);
   if (dtype == DMPC_F32) return traj_impl<float>(h, T, B, n, m, dynamics, d_x0, d_u, d_F, d_f, h_dyn_params, d_x, d_Fout, d_fout, st);
   return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
+}
+
+int dmpc_boxddp_workspace_bytes(int dtype, int T, int B, int n, int m, size_t* bytes) {
+  if (!bytes || T < 1 || B < 1 || n < 1 || m < 1) return DMPC_ERR_BAD_SHAPE;
+  if (dtype != DMPC_F64 && dtype != DMPC_F32) return DMPC_ERR_UNSUPPORTED;
+  *bytes = box_ws(dtype == DMPC_F64 ? 8 : 4, T, B, n, m).total;
+  return DMPC_OK;
+}
+
+int dmpc_boxddp_solve(dmpc_handle h, int dtype, int T, int B, int n, int m, const void* d_x_init, const void* d_C,
+                      const void* d_c, const void* d_lower, const void* d_upper, int dynamics, const void* d_F, int F_T,
+                      const void* d_f, const double* h_dyn_params, const void* d_u_init, const dmpc_boxddp_opts* opts,
+                      void* d_ws, size_t ws_bytes, void* d_x_best, void* d_u_best, void* d_costs_best, void* d_du_best,
+                      void* d_du_last, void* d_F_lin, void* d_f_lin, int* h_n_iter, int* h_status, int* h_flags,
+                      void* stream) {
+  if (!h) return DMPC_ERR_NULL;
+  if (T < 1 || B < 1 || n < 1 || m < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "T,B,n,m must be >= 1");
+  if (!opts || opts->max_iter < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "boxddp: opts with max_iter >= 1 required");
+  if (!d_x_init || !d_C || !d_c || !d_lower || !d_upper || !d_u_init || !d_ws || !d_x_best || !d_u_best || !d_costs_best || !d_du_best)
+    return fail(h, DMPC_ERR_NULL, "boxddp: required buffer is NULL");
+  if (dynamics == DMPC_DYN_LINEAR && T > 1 && (!d_F || (F_T != T - 1 && F_T != T))) return fail(h, DMPC_ERR_BAD_SHAPE, "boxddp: linear dynamics need F with T-1 or T rows");
+  if (dynamics == DMPC_DYN_PENDULUM && (n != 3 || m != 1 || !h_dyn_params || !d_F_lin || !d_f_lin))
+    return fail(h, DMPC_ERR_BAD_SHAPE, "boxddp: pendulum needs n=3, m=1, params and F_lin/f_lin outputs");
+  if (dynamics != DMPC_DYN_LINEAR && dynamics != DMPC_DYN_PENDULUM) return fail(h, DMPC_ERR_UNSUPPORTED, "dynamics selector");
+  size_t need = 0;
+  if (dmpc_boxddp_workspace_bytes(dtype, T, B, n, m, &need)) return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
+  if (ws_bytes < need) return fail(h, DMPC_ERR_BAD_SHAPE, "boxddp: workspace too small (dmpc_boxddp_workspace_bytes)");
+  if (set_dev(h)) return DMPC_ERR_CUDA;
+  cudaStream_t st = pick(h, stream);
+  if (dtype == DMPC_F64) return boxddp_impl<double>(h, dtype, T, B, n, m, d_x_init, d_C, d_c, d_lower, d_upper, dynamics, d_F, F_T, d_f, h_dyn_params, d_u_init, opts, d_ws, d_x_best, d_u_best, d_costs_best, d_du_best, d_du_last, d_F_lin, d_f_lin, h_n_iter, h_status, h_flags, st);
+  return boxddp_impl<float>(h, dtype, T, B, n, m, d_x_init, d_C, d_c, d_lower, d_upper, dynamics, d_F, F_T, d_f, h_dyn_params, d_u_init, opts, d_ws, d_x_best, d_u_best, d_costs_best, d_du_best, d_du_last, d_F_lin, d_f_lin, h_n_iter, h_status, h_flags, st);
 }
 
 }  // extern "C"

@@ -33,7 +33,7 @@ class BoxDDP(LinkBase):
     def __init__(self, T, u_lower, u_upper, n_batch, n_state, n_ctrl, u_init, eps=1e-5, not_improved_lim=5,
                  line_search_decay=0.2, max_line_search_iter=10, best_cost_eps=1e-4, max_iter=10,
                  detach_unconverged=True, exit_unconverged=True, verbose=False, ilqr_verbose=False,
-                 update_dynamics=True, coupling=None, device=0):
+                 update_dynamics=True, coupling=None, device=0, device_loop=True):
         if LinkBase is not object:
             super().__init__()
         self.T, self.n_batch, self.n_state, self.n_ctrl = int(T), int(n_batch), int(n_state), int(n_ctrl)
@@ -52,6 +52,9 @@ class BoxDDP(LinkBase):
         self.update_dynamics = update_dynamics
         self.coupling = coupling
         self.device = device
+        # device_loop: run the whole iLQR loop through dmpc_boxddp_solve (tensors stay in HBM, one 32-byte status
+        # read per iteration).  verbose=True needs the per-iteration table of the reference and uses the host loop.
+        self.device_loop = device_loop
         shape = (self.T, self.n_batch, self.n_ctrl)
         if isinstance(u_lower, float) or np.isscalar(u_lower):      # reference :68-90 (Q9)
             self.u_lower = np.full(shape, float(u_lower))
@@ -82,6 +85,45 @@ class BoxDDP(LinkBase):
             return dx.download(), Fo.download()[:T - 1], fo.download()[:T - 1]
         raise NotImplementedError("dynamics must be util.LinDx or a PendulumDx (SURVEY.md H3)")
 
+    def _solve_on_device(self, ctx, x_init, C_arr, c_arr, true_dyn, u):
+        """The loop of reference :121-230 in one C-ABI call.  Returns (best, du_last, n_iter, status, F_lin, f_lin)."""
+        from mpc_step import resolve_coupling, MAX_LS_TRIALS
+        T, B, n, m, s = self.T, self.n_batch, self.n_state, self.n_ctrl, self.n_sc
+        dt = np.float64
+        Tm = max(T - 1, 1)
+        if isinstance(true_dyn, LinDx):
+            dyn, params = _native.DYN_LINEAR, None
+            F_h, f_h = true_dyn.F, true_dyn.f
+            dF, F_T = ctx.to_device(F_h), F_h.shape[0]
+            df = None if f_h is None else ctx.to_device(f_h[:T - 1])
+            F_lin = f_lin = None
+        elif is_pendulum(true_dyn):
+            dyn, params = _native.DYN_PENDULUM, pendulum_params(true_dyn)
+            dF = df = None
+            F_T = T - 1
+            F_lin, f_lin = ctx.empty((Tm, B, n, s), dt), ctx.empty((Tm, B, n), dt)
+        else:
+            raise NotImplementedError("dynamics must be util.LinDx or a PendulumDx (SURVEY.md H3)")
+        coupling = resolve_coupling(self.coupling, B, n, m)
+        o = dict(x=ctx.empty((T, B, n), dt), u=ctx.empty((T, B, m), dt), costs=ctx.empty((B,), dt),
+                 du=ctx.empty((B,), dt), du_last=ctx.empty((B,), dt))
+        n_iter, status, flags = ctx.boxddp_solve(
+            dt, T, B, n, m, ctx.to_device(x_init), ctx.to_device(C_arr), ctx.to_device(c_arr), ctx.to_device(self.u_lower),
+            ctx.to_device(self.u_upper), dyn, dF, F_T, df, params, ctx.to_device(u), self.eps, self.best_cost_eps,
+            self.ls_decay, self.not_improved_lim, self.max_iter, MAX_LS_TRIALS,
+            _native.COUPLING_BATCH if coupling == "batch" else _native.COUPLING_ELEMENT,
+            o["x"], o["u"], o["costs"], o["du"], o["du_last"], F_lin, f_lin)
+        if flags & _native.FLAG_QP_NOT_CONVERGED:
+            warnings.warn("Projected Newton Quadratic Programming warning: Did not converge")
+        if flags & _native.FLAG_LS_CAPPED:
+            warnings.warn("MPCstep line search hit the %d-trial cap" % MAX_LS_TRIALS)
+        best = dict(x=o["x"].download(), u=o["u"].download(), costs=o["costs"].download(), full_du_norm=o["du"].download())
+        if F_lin is not None:
+            large_f, f = F_lin.download()[:T - 1], f_lin.download()[:T - 1]
+        else:
+            large_f, f = true_dyn.F, true_dyn.f
+        return best, o["du_last"].download(), n_iter, {0: "max_iter", 1: "converged", 2: "not_improved"}[status], large_f, f
+
     def forward(self, inputs):
         x_init, cost, dynamics = inputs
         T, B, n, m = self.T, self.n_batch, self.n_state, self.n_ctrl
@@ -109,7 +151,11 @@ class BoxDDP(LinkBase):
         for_out = None
         status = "max_iter"
         n_iter = 0
-        for i in range(self.max_iter):
+        on_device = self.device_loop and not self.verbose and not self.ilqr_verbose
+        if on_device:
+            best, du_last, n_iter, status, large_f, f = self._solve_on_device(ctx, x_init, C_arr, c_arr, true_dyn, u)
+            print({"converged": "Converged", "not_improved": "Not improved lim", "max_iter": "Not Converged "}[status])
+        for i in range(0 if on_device else self.max_iter):
             n_iter = i + 1
             x, large_f, f = self._rollout(ctx, x_init, u, true_dyn)
             step = MPCstep(controls=u, T=T, u_upper=self.u_upper, u_lower=self.u_lower, n_batch=B, n_state=n,
@@ -144,7 +190,9 @@ class BoxDDP(LinkBase):
                 print("Not Converged ")
         x, u = best["x"], best["u"]
         # linearise at the returned point (reference :235-242) and attach the differentiable graph
-        _, large_f, f = self._rollout(ctx, x[0], u, true_dyn)
+        if not on_device:
+            _, large_f, f = self._rollout(ctx, x[0], u, true_dyn)
+            du_last = for_out.full_du_norm
         final = MPCstep(controls=u, T=T, u_upper=self.u_upper, u_lower=self.u_lower, n_batch=B, n_state=n, n_ctrl=m,
                         current_states=x, true_cost=true_cost, true_dynamics=true_dyn, ls_decay=self.ls_decay,
                         max_ls_iter=self.max_ls_iter, verbose=self.ilqr_verbose, need_expand=True,
@@ -167,13 +215,13 @@ class BoxDDP(LinkBase):
                 print("LQR Warning: All examples did not converge to a fixed point.")
                 print("Detaching and *not* backpropping through the bad examples.")
             warnings.warn("LQR Warning: All examples did not converge to a fixed point.")
-            detach_mask = for_out.full_du_norm < self.eps
+            detach_mask = du_last < self.eps
             Ix = np.broadcast_to(detach_mask[None, :, None], (T, B, n)).astype(np.float64)
             Iu = np.broadcast_to(detach_mask[None, :, None], (T, B, m)).astype(np.float64)
             x_new = x_new * Ix + copy.deepcopy(to_xp(x_new)) * (1.0 - Ix)
             u_new = u_new * Iu + copy.deepcopy(to_xp(u_new)) * (1.0 - Iu)
         self.info = dict(n_iter=n_iter, status=status, detach_mask=detach_mask, full_du_norm_best=best["full_du_norm"],
-                         full_du_norm_last=for_out.full_du_norm, F_lin=large_f, f_lin=f)
+                         full_du_norm_last=du_last, F_lin=large_f, f_lin=f)
         return x_new, u_new, best["costs"]
 
     if LinkBase is object:

@@ -200,6 +200,45 @@ int dmpc_get_traj(dmpc_handle h, int dtype, int T, int B, int n, int m, int dyna
                   const void* d_x0, const void* d_u, const void* d_F, const void* d_f,
                   const double* h_dyn_params, void* d_x, void* d_Fout, void* d_fout, void* stream);
 
+/*
+ * BoxDDP.forward (mpc/box_ddp.py:93-291): the box-constrained iLQR outer loop, device resident.
+ * Per iteration: rollout of the nominal controls + linearisation (util.get_traj :123,
+ * approximate.linearize_dynamics :126-131 - analytic for the pendulum), one MPCstep.forward (:173-193),
+ * per-element best trajectory (:195-209, costs <= best + best_cost_eps), then the reference's batch-global exits:
+ * max(full_du_norm) < eps -> converged (:223); the shared n_not_improved counter > not_improved_lim (:227).
+ * full_du_norm keeps the reference's batch-mixing reshape (mpc_step.py:261-263) with numpy's summation order.
+ * The host reads one 32-byte status record per iteration; all tensors stay in HBM.
+ *   inputs : d_x_init[B,n], d_C[T,B,s,s], d_c[T,B,s] (the QuadCost, also the true cost), d_lower/d_upper[T,B,m],
+ *            dynamics selector (+ d_F[F_T,B,n,s], d_f[T-1,B,n] or NULL for DMPC_DYN_LINEAR; h_dyn_params (g,m,l)
+ *            for DMPC_DYN_PENDULUM), d_u_init[T,B,m] (not modified)
+ *   outputs: d_x_best[T,B,n], d_u_best[T,B,m], d_costs_best[B], d_du_best[B] (full_du_norm at the best step),
+ *            d_du_last[B] (of the last step; may be NULL), d_F_lin[T-1,B,n,s], d_f_lin[T-1,B,n] = linearisation
+ *            at the returned point (pendulum only, :235-242; NULL for linear dynamics),
+ *            *h_n_iter, *h_status (DMPC_BOXDDP_*), *h_flags (OR of the per-element DMPC_FLAG_* over all steps)
+ *   d_ws   : caller-owned workspace of dmpc_boxddp_workspace_bytes() bytes
+ * Returns DMPC_ERR_NONFINITE where the reference's NaN asserts would fire (mpc_step.py:284-285).
+ */
+typedef struct {
+  double eps;               /* box_ddp.py:27 eps */
+  double best_cost_eps;
+  double ls_decay;          /* line_search_decay */
+  int not_improved_lim;
+  int max_iter;
+  int max_ls_trials;        /* safety cap of the per-element line search (<= 0: 64) */
+  int coupling;             /* DMPC_COUPLING_* */
+} dmpc_boxddp_opts;
+
+enum { DMPC_BOXDDP_MAX_ITER = 0, DMPC_BOXDDP_CONVERGED = 1, DMPC_BOXDDP_NOT_IMPROVED = 2 };
+
+int dmpc_boxddp_workspace_bytes(int dtype, int T, int B, int n, int m, size_t* bytes);
+int dmpc_boxddp_solve(dmpc_handle h, int dtype, int T, int B, int n, int m,
+                      const void* d_x_init, const void* d_C, const void* d_c,
+                      const void* d_lower, const void* d_upper,
+                      int dynamics, const void* d_F, int F_T, const void* d_f, const double* h_dyn_params,
+                      const void* d_u_init, const dmpc_boxddp_opts* opts, void* d_ws, size_t ws_bytes,
+                      void* d_x_best, void* d_u_best, void* d_costs_best, void* d_du_best, void* d_du_last,
+                      void* d_F_lin, void* d_f_lin, int* h_n_iter, int* h_status, int* h_flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,3 +122,68 @@ def test_boxddp_pendulum_like_il_env():
     # see DESIGN.md §6); every non-degenerate decision matches and the result agrees to ~1e-6.
     assert rel_err(arr(x), g["x"]) < 1e-5 and rel_err(arr(u), g["u"]) < 1e-5
     assert rel_err(costs, g["costs"]) < 1e-9
+
+
+@pytest.mark.parametrize("case", ["lindx", "pendulum"])
+def test_boxddp_device_loop_equals_host_loop(case, capsys):
+    """dmpc_boxddp_solve (whole iLQR loop on the device, reference mpc/box_ddp.py:121-230) must take exactly the
+    decisions of the per-iteration host loop: same iterates, same best tracking, same exit."""
+    from box_ddp import BoxDDP
+    from util import QuadCost, LinDx
+    from pendulum_dx import PendulumDx
+    if case == "lindx":
+        g = load_golden("ddp_n3m2")
+        n, m = int(g["n"]), int(g["m"])
+        T, B = g["C"].shape[:2]
+        b = float(g["bound"])
+        kw = dict(T=T, u_lower=-b, u_upper=b, n_batch=B, n_state=n, n_ctrl=m, u_init=None, eps=1e-7, max_iter=30,
+                  line_search_decay=0.2, max_line_search_iter=10)
+        inputs = (g["x0"], QuadCost(g["C"], g["c"]), LinDx(g["F"], g["f"]))
+    else:
+        g = load_golden("pendulum_ddp")
+        dx = PendulumDx()
+        T, B = 20, g["x0"].shape[0]
+        kw = dict(T=T, u_lower=dx.lower, u_upper=dx.upper, n_batch=B, n_state=3, n_ctrl=1, u_init=None, eps=dx.mpc_eps,
+                  max_iter=500, exit_unconverged=False, detach_unconverged=True, line_search_decay=dx.linesearch_decay,
+                  max_line_search_iter=dx.max_linesearch_iter, update_dynamics=True)
+        inputs = (g["x0"], QuadCost(g["Q"], g["p"]), dx)
+    res = {}
+    for mode in (True, False):
+        solver = BoxDDP(device_loop=mode, **kw)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x, u, costs = solver(inputs)
+        res[mode] = (arr(x), arr(u), np.asarray(costs), solver.info)
+    capsys.readouterr()
+    (xd, ud, cd, idv), (xh, uh, ch, ih) = res[True], res[False]
+    assert idv["n_iter"] == ih["n_iter"] and idv["status"] == ih["status"]
+    assert np.array_equal(xd, xh) and np.array_equal(ud, uh) and np.array_equal(cd, ch)
+    assert np.array_equal(idv["full_du_norm_best"], ih["full_du_norm_best"])      # numpy's pairwise summation order
+    assert np.array_equal(idv["full_du_norm_last"], ih["full_du_norm_last"])
+    assert np.array_equal(idv["F_lin"], ih["F_lin"])
+
+
+def test_boxddp_device_loop_scrambled_norm_long_rows():
+    """T*m > 128 exercises the recursive branch of numpy's pairwise summation in scrambled_norm_kernel."""
+    from box_ddp import BoxDDP
+    from util import QuadCost, LinDx
+    rs = np.random.RandomState(5)
+    T, B, n, m = 40, 6, 4, 4            # T*m = 160
+    s = n + m
+    L = 0.3 * rs.randn(T, B, s, s)
+    C = L @ np.transpose(L, (0, 1, 3, 2)) + np.eye(s)
+    c = rs.randn(T, B, s)
+    F = np.repeat(np.concatenate((0.9 * np.eye(n) + 0.05 * rs.randn(B, n, n), rs.randn(B, n, m)), axis=2)[None], T - 1, axis=0)
+    f = 0.1 * rs.randn(T - 1, B, n)
+    x0 = rs.randn(B, n)
+    out = {}
+    for mode in (True, False):
+        solver = BoxDDP(T=T, u_lower=-0.5, u_upper=0.5, n_batch=B, n_state=n, n_ctrl=m, u_init=None, eps=1e-9, max_iter=4,
+                        device_loop=mode)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x, u, costs = solver((x0, QuadCost(C, c), LinDx(F, f)))
+        out[mode] = (arr(u), solver.info["full_du_norm_last"], solver.info["full_du_norm_best"], solver.info["n_iter"])
+    assert out[True][3] == out[False][3]
+    assert np.array_equal(out[True][0], out[False][0])
+    assert np.array_equal(out[True][1], out[False][1]) and np.array_equal(out[True][2], out[False][2])
