@@ -52,6 +52,9 @@ SIGNATURES = {
     "dmpc_mpc_step_backward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i] + [_vp] * 15 + [_vp]),
     "dmpc_lqr_active_solve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dmpc_get_traj": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(_d), _vp, _vp, _vp, _vp]),
+    "dmpc_reduced_grad_elems": (_sz, [_i, _i]),
+    "dmpc_lqr_adjoint_reduced": (_i, [_vp, _i, _i, _i, _i, _i] + [_vp] * 13 + [_i, _vp]),
+    "dmpc_mpc_step_backward_reduced": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i] + [_vp] * 13 + [_vp]),
     "dmpc_boxddp_workspace_bytes": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(_sz)]),
     "dmpc_boxddp_solve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, ctypes.POINTER(_d), _vp,
                                _vp, _vp, _sz] + [_vp] * 7 + [ctypes.POINTER(_i)] * 3 + [_vp]),
@@ -292,6 +295,33 @@ class Context:
     def get_traj(self, dtype, T, B, n, m, dynamics, x0, u, F, f, dyn_params, x, Fout=None, fout=None, stream=None):
         self._check(self.lib.dmpc_get_traj(self.h, dtype_code(dtype), T, B, n, m, dynamics, _p(x0), _p(u), _p(F), _p(f),
                                            self._dynp(dyn_params), _p(x), _p(Fout), _p(fout), stream))
+
+    @staticmethod
+    def split_reduced(sums, n, m):
+        """(sum dC [s,s], sum dc [s], sum dF [n,s], sum df [n]) views of a dmpc_*_reduced result."""
+        s = n + m
+        o = 0
+        out = []
+        for shape in ((s, s), (s,), (n, s), (n,)):
+            sz = int(np.prod(shape))
+            out.append(sums[o:o + sz].reshape(shape))
+            o += sz
+        return tuple(out)
+
+    def lqr_adjoint_reduced(self, dtype, T, B, n, m, C, c, F, x, u, gx, gu, Ks, fac, ws_dtau, ws_partials, dx0, sums,
+                            flags=ADJ_STRICT_REFERENCE, stream=None):
+        self._check(self.lib.dmpc_lqr_adjoint_reduced(
+            self.h, dtype_code(dtype), T, B, n, m, _p(C), _p(c), _p(F), _p(x), _p(u), _p(gx), _p(gu), _p(Ks), _p(fac),
+            _p(ws_dtau), _p(ws_partials), _p(dx0), _p(sums), flags, stream))
+
+    def mpc_step_backward_reduced(self, dtype, T, B, n, m, C, c, F, F_T, x, u, lower, upper, gx, gu, ws_Ks, ws_ks,
+                                  ws_dtau, active, ws_partials, dx0, sums, stream=None):
+        self._check(self.lib.dmpc_mpc_step_backward_reduced(
+            self.h, dtype_code(dtype), T, B, n, m, _p(C), _p(c), _p(F), F_T, _p(x), _p(u), _p(lower), _p(upper),
+            _p(gx), _p(gu), _p(ws_Ks), _p(ws_ks), _p(ws_dtau), _p(active), _p(ws_partials), _p(dx0), _p(sums), stream))
+
+    def reduced_grad_elems(self, n, m):
+        return int(self.lib.dmpc_reduced_grad_elems(n, m))
 
     def boxddp_solve(self, dtype, T, B, n, m, x_init, C, c, lower, upper, dynamics, F, F_T, f, dyn_params, u_init,
                      eps, best_cost_eps, ls_decay, not_improved_lim, max_iter, max_ls_trials, coupling,

@@ -53,7 +53,7 @@ template <typename R>
 static int lqr_adjoint_impl(dmpc_handle h, int T, int B, int n, int m, const void* C, const void* c, const void* F,
                             const void* x, const void* u, const void* gx, const void* gu, const void* Ks,
                             const void* fac, void* dx0, void* dC, void* dc, void* dF, void* df, int flags,
-                            cudaStream_t st) {
+                            cudaStream_t st, void* partials = nullptr, void* sums = nullptr) {
   DtauParams<R> d;
   d.T = T; d.B = B; d.n = n; d.m = m;
   d.F = (const R*)F; d.gx = (const R*)gx; d.gu = (const R*)gu; d.Ks = (const R*)Ks; d.fac = (const R*)fac;
@@ -67,8 +67,13 @@ static int lqr_adjoint_impl(dmpc_handle h, int T, int B, int n, int m, const voi
   a.C = (const R*)C; a.c = (const R*)c; a.F = (const R*)F; a.x = (const R*)x; a.u = (const R*)u;
   a.dtau = (const R*)dc; a.gx = (const R*)gx; a.gu = (const R*)gu;
   a.dx0 = (R*)dx0; a.dC = (R*)dC; a.dc = (R*)dc; a.dF = (R*)dF; a.df = (R*)df;
+  if (partials) { a.flags |= ADJ_REDUCE_TB; a.red = (R*)partials; }
   rc = launch_adjoint_out<R>(a, st, &h->launches);
-  if (rc) h->err = "adjoint_out launch failed";
+  if (rc) { h->err = "adjoint_out launch failed"; return rc; }
+  if (partials) {
+    rc = launch_reduce_partials<R>((const R*)partials, B, adj_red_elems(n, m), (R*)sums, st, &h->launches);
+    if (rc) h->err = "reduce_partials launch failed";
+  }
   return rc;
 }
 
@@ -102,7 +107,8 @@ template <typename R>
 static int mpc_backward_impl(dmpc_handle h, int T, int B, int n, int m, const void* C, const void* c, const void* F,
                              int F_T, const void* x, const void* u, const void* lo, const void* hi, const void* gx,
                              const void* gu, void* wsK, void* wsk, void* wsd, void* act, void* dx0, void* dC,
-                             void* dc, void* dF, void* df, cudaStream_t st) {
+                             void* dc, void* dF, void* df, cudaStream_t st, void* partials = nullptr,
+                             void* sums = nullptr) {
   int rc = launch_active_mask<R>((const R*)u, (const R*)lo, (const R*)hi, (unsigned char*)act, (size_t)T * B * m, st, &h->launches);
   if (rc) { h->err = "active_mask launch failed"; return rc; }
   if (cudaMemsetAsync(dx0, 0, (size_t)B * n * sizeof(R), st) != cudaSuccess) return DMPC_ERR_CUDA;
@@ -123,8 +129,13 @@ static int mpc_backward_impl(dmpc_handle h, int T, int B, int n, int m, const vo
   a.C = (const R*)C; a.c = (const R*)c; a.F = (const R*)F; a.x = (const R*)x; a.u = (const R*)u;
   a.dtau = (const R*)wsd; a.gx = (const R*)gx; a.gu = (const R*)gu;
   a.dx0 = (R*)dx0; a.dC = (R*)dC; a.dc = (R*)dc; a.dF = (R*)dF; a.df = (R*)df;
+  if (partials) { a.flags |= ADJ_REDUCE_TB; a.red = (R*)partials; }
   rc = launch_adjoint_out<R>(a, st, &h->launches);
-  if (rc) h->err = "adjoint_out launch failed";
+  if (rc) { h->err = "adjoint_out launch failed"; return rc; }
+  if (partials) {
+    rc = launch_reduce_partials<R>((const R*)partials, B, adj_red_elems(n, m), (R*)sums, st, &h->launches);
+    if (rc) h->err = "reduce_partials launch failed";
+  }
   return rc;
 }
 
@@ -496,6 +507,41 @@ int dmpc_boxddp_solve(dmpc_handle h, int dtype, int T, int B, int n, int m, cons
   cudaStream_t st = pick(h, stream);
   if (dtype == DMPC_F64) return boxddp_impl<double>(h, dtype, T, B, n, m, d_x_init, d_C, d_c, d_lower, d_upper, dynamics, d_F, F_T, d_f, h_dyn_params, d_u_init, opts, d_ws, d_x_best, d_u_best, d_costs_best, d_du_best, d_du_last, d_F_lin, d_f_lin, h_n_iter, h_status, h_flags, st);
   return boxddp_impl<float>(h, dtype, T, B, n, m, d_x_init, d_C, d_c, d_lower, d_upper, dynamics, d_F, F_T, d_f, h_dyn_params, d_u_init, opts, d_ws, d_x_best, d_u_best, d_costs_best, d_du_best, d_du_last, d_F_lin, d_f_lin, h_n_iter, h_status, h_flags, st);
+}
+
+size_t dmpc_reduced_grad_elems(int n, int m) { return (size_t)adj_red_elems(n, m); }
+
+int dmpc_lqr_adjoint_reduced(dmpc_handle h, int dtype, int T, int B, int n, int m, const void* d_C, const void* d_c,
+                             const void* d_F, const void* d_x, const void* d_u, const void* d_gx, const void* d_gu,
+                             const void* d_Ks, const void* d_fac, void* d_ws_dtau, void* d_ws_partials, void* d_dx0,
+                             void* d_sums, int flags, void* stream) {
+  if (!h) return DMPC_ERR_NULL;
+  if (T < 1 || B < 1 || n < 1 || m < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "T,B,n,m must be >= 1");
+  if (!d_C || !d_c || !d_x || !d_u || !d_gx || !d_gu || !d_Ks || !d_fac || !d_ws_dtau || !d_ws_partials || !d_dx0 || !d_sums || (T > 1 && !d_F))
+    return fail(h, DMPC_ERR_NULL, "lqr_adjoint_reduced: required buffer is NULL");
+  if (set_dev(h)) return DMPC_ERR_CUDA;
+  cudaStream_t st = pick(h, stream);
+  if (dtype == DMPC_F64) return lqr_adjoint_impl<double>(h, T, B, n, m, d_C, d_c, d_F, d_x, d_u, d_gx, d_gu, d_Ks, d_fac, d_dx0, nullptr, d_ws_dtau, nullptr, nullptr, flags, st, d_ws_partials, d_sums);
+  if (dtype == DMPC_F32) return lqr_adjoint_impl<float>(h, T, B, n, m, d_C, d_c, d_F, d_x, d_u, d_gx, d_gu, d_Ks, d_fac, d_dx0, nullptr, d_ws_dtau, nullptr, nullptr, flags, st, d_ws_partials, d_sums);
+  return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
+}
+
+int dmpc_mpc_step_backward_reduced(dmpc_handle h, int dtype, int T, int B, int n, int m, const void* d_C, const void* d_c,
+                                   const void* d_F, int F_T, const void* d_x, const void* d_u, const void* d_lower,
+                                   const void* d_upper, const void* d_gx, const void* d_gu, void* d_ws_Ks, void* d_ws_ks,
+                                   void* d_ws_dtau, void* d_active, void* d_ws_partials, void* d_dx0, void* d_sums,
+                                   void* stream) {
+  if (!h) return DMPC_ERR_NULL;
+  if (T < 1 || B < 1 || n < 1 || m < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "T,B,n,m must be >= 1");
+  if (T > 1 && F_T != T - 1 && F_T != T) return fail(h, DMPC_ERR_BAD_SHAPE, "F_hat must have T-1 or T time rows");
+  if (!d_C || !d_c || (T > 1 && !d_F) || !d_x || !d_u || !d_lower || !d_upper || !d_ws_Ks || !d_ws_ks || !d_ws_dtau ||
+      !d_active || !d_ws_partials || !d_dx0 || !d_sums)
+    return fail(h, DMPC_ERR_NULL, "mpc_step_backward_reduced: required buffer is NULL");
+  if (set_dev(h)) return DMPC_ERR_CUDA;
+  cudaStream_t st = pick(h, stream);
+  if (dtype == DMPC_F64) return mpc_backward_impl<double>(h, T, B, n, m, d_C, d_c, d_F, F_T, d_x, d_u, d_lower, d_upper, d_gx, d_gu, d_ws_Ks, d_ws_ks, d_ws_dtau, d_active, d_dx0, nullptr, nullptr, nullptr, nullptr, st, d_ws_partials, d_sums);
+  if (dtype == DMPC_F32) return mpc_backward_impl<float>(h, T, B, n, m, d_C, d_c, d_F, F_T, d_x, d_u, d_lower, d_upper, d_gx, d_gu, d_ws_Ks, d_ws_ks, d_ws_dtau, d_active, d_dx0, nullptr, nullptr, nullptr, nullptr, st, d_ws_partials, d_sums);
+  return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
 }
 
 }  // extern "C"

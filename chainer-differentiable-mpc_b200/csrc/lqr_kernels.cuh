@@ -25,6 +25,8 @@ enum AdjFlags : int {
   ADJ_QUIRK_DF = 2,     // df[t] = dlambda[t] instead of dlambda[t+1] (differentiable_lqr.py:133)
   ADJ_NEGATE = 4,       // MPCstep.backward sign convention (mpc_step.py:387-446)
   ADJ_NEG_RHS = 8,      // dlambda uses -d_taus_x as rhs (mpc_step.py:417)
+  ADJ_REDUCE_TB = 16,   // do not materialise dC,dc,dF,df: sum them over t in shared memory and emit one partial
+                        // record per element (backward of util.expand_time_batch, util.py:361-377, fused in)
 };
 
 template <typename R>
@@ -424,12 +426,15 @@ struct AdjOutParams {
   const R* dtau;               // [T,B,s] (may alias dc when !ADJ_NEGATE)
   const R* gx; const R* gu;    // upstream grads (nullable -> zeros)
   R* dx0; R* dC; R* dc; R* dF; R* df;   // df nullable
+  R* red;                      // ADJ_REDUCE_TB: [B][s*s + s + n*s + n] per-element sums over t (dC | dc | dF | df)
 };
 
-struct AdjLayout { int oC, oc, oF, otau, odtau, og, stage, st0, st1, lam, dlam, lamn, dlamn, total, stride; };
+struct AdjLayout { int oC, oc, oF, otau, odtau, og, stage, st0, st1, lam, dlam, lamn, dlamn, red, total, stride; };
+
+__host__ __device__ inline int adj_red_elems(int n, int m) { const int s = n + m; return s * s + s + n * s + n; }
 
 template <typename R>
-__host__ __device__ inline AdjLayout adj_layout(int n, int m) {
+__host__ __device__ inline AdjLayout adj_layout(int n, int m, bool reduce = false) {
   const int W = 16 / (int)sizeof(R);
   const int s = n + m;
   AdjLayout L;
@@ -448,6 +453,7 @@ __host__ __device__ inline AdjLayout adj_layout(int n, int m) {
   L.dlam = o; o += rup(n, W);
   L.lamn = o; o += rup(n, W);
   L.dlamn = o; o += rup(n, W);
+  L.red = o; if (reduce) o += rup(adj_red_elems(n, m), W);
   L.total = o;
   const int line = 128 / (int)sizeof(R);
   L.stride = rup(o, line) + W;
@@ -467,9 +473,12 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
   int e = blockIdx.x * epb + eloc;
   const bool valid = e < B;
   if (!valid) e = B - 1;
-  const AdjLayout L = adj_layout<R>(n, m);
+  const bool reduce = (p.flags & ADJ_REDUCE_TB) != 0;
+  const AdjLayout L = adj_layout<R>(n, m, reduce);
   R* sm = reinterpret_cast<R*>(smem_raw) + (size_t)eloc * L.stride;
   R* lam = sm + L.lam; R* dlam = sm + L.dlam; R* lamn = sm + L.lamn; R* dlamn = sm + L.dlamn;
+  R* rC = sm + L.red; R* rc = rC + s * s; R* rF = rc + s; R* rf = rF + n * s;     // per-element sums over t
+  if (reduce) for (int o = g.lane; o < adj_red_elems(n, m); o += G) rC[o] = R(0);
   const size_t tb = (size_t)B;
   const int nxoff = rup(n, 16 / (int)sizeof(R));
   const bool neg = (p.flags & ADJ_NEGATE) != 0;
@@ -504,10 +513,12 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
       R* dFg = p.dF + idx * n * s;
       for (int o = g.lane; o < n * s; o += G) {
         const int i = o / s, j = o - i * s;
-        dFg[o] = sgn * (dlam[i] * tau(j) + lam[i] * dt[j]);
+        const R v = sgn * (dlam[i] * tau(j) + lam[i] * dt[j]);
+        if (reduce) rF[o] += v; else dFg[o] = v;
       }
-      if (p.df && !(p.flags & ADJ_QUIRK_DF)) {
-        for (int o = g.lane; o < n; o += G) p.df[idx * n + o] = sgn * dlam[o];
+      if (!(p.flags & ADJ_QUIRK_DF)) {
+        if (reduce) { for (int o = g.lane; o < n; o += G) rf[o] += sgn * dlam[o]; }
+        else if (p.df) { for (int o = g.lane; o < n; o += G) p.df[idx * n + o] = sgn * dlam[o]; }
       }
     }
     // lam_t, dlam_t
@@ -529,25 +540,53 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
       for (int o = g.lane; o < s * s; o += G) {
         const int i = o / s, j = o - i * s;
         const R a = dt[i] * tau(j), b = tau(i) * dt[j];
-        dCg[o] = quirk ? (R(0.5) * a + b) : (sgn * R(0.5) * (a + b));
+        const R v = quirk ? (R(0.5) * a + b) : (sgn * R(0.5) * (a + b));
+        if (reduce) rC[o] += v; else dCg[o] = v;
       }
-      if (neg || p.dc != p.dtau) for (int o = g.lane; o < s; o += G) p.dc[idx * s + o] = sgn * dt[o];
+      if (reduce) { for (int o = g.lane; o < s; o += G) rc[o] += sgn * dt[o]; }
+      else if (neg || p.dc != p.dtau) for (int o = g.lane; o < s; o += G) p.dc[idx * s + o] = sgn * dt[o];
     }
     g.sync();
     for (int o = g.lane; o < n; o += G) { lam[o] = lamn[o]; dlam[o] = dlamn[o]; }
     if (valid) {
-      if (p.df && (p.flags & ADJ_QUIRK_DF) && t < T - 1)
-        for (int o = g.lane; o < n; o += G) p.df[idx * n + o] = sgn * dlamn[o];
+      if ((p.flags & ADJ_QUIRK_DF) && t < T - 1) {
+        if (reduce) { for (int o = g.lane; o < n; o += G) rf[o] += sgn * dlamn[o]; }
+        else if (p.df) { for (int o = g.lane; o < n; o += G) p.df[idx * n + o] = sgn * dlamn[o]; }
+      }
       if (t == 0) for (int o = g.lane; o < n; o += G) p.dx0[(size_t)e * n + o] = sgn * dlamn[o];
     }
     g.sync();
     st ^= 1;
+  }
+  if (reduce) {   // every (i,j) is owned by one lane for the whole horizon: no barrier needed before the write-out
+    if (valid) {
+      const int rsz = adj_red_elems(n, m);
+      R* out = p.red + (size_t)e * rsz;
+      for (int o = g.lane; o < rsz; o += G) out[o] = rC[o];
+    }
+    return;
   }
   // zero-fill the T-th row of dF when F was given with T rows (Q8, mpc_step.py:428)
   if (p.F_T == T && valid) {
     R* dFg = p.dF + ((size_t)(T - 1) * tb + e) * n * s;
     for (int o = g.lane; o < n * s; o += G) dFg[o] = R(0);
   }
+}
+
+// Second stage of ADJ_REDUCE_TB: out[o] = sum_e red[e][o] in a fixed order (lane-strided partial sums, then a
+// shuffle tree) - deterministic, unlike atomics.  One warp per output element.
+template <typename R>
+__global__ void reduce_partials_kernel(const R* red, int B, int rsz, R* out) {
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= rsz) return;
+  const int lane = threadIdx.x & 31;
+  R a0 = R(0), a1 = R(0);
+  int e = lane;
+  for (; e + 32 < B; e += 64) { a0 += red[(size_t)e * rsz + o]; a1 += red[(size_t)(e + 32) * rsz + o]; }
+  if (e < B) a0 += red[(size_t)e * rsz + o];
+  R a = a0 + a1;
+  for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+  if (lane == 0) out[o] = a;
 }
 
 }  // namespace dmpc

@@ -136,7 +136,7 @@ int launch_lqr_dtau(const DtauParams<R>& p, cudaStream_t st, long long* nl) {
 template <typename R>
 int launch_adjoint_out(const AdjOutParams<R>& p, cudaStream_t st, long long* nl) {
   const ShapeInfo si = pick_shape_impl(p.n, p.m);
-  const AdjLayout L = adj_layout<R>(p.n, p.m);
+  const AdjLayout L = adj_layout<R>(p.n, p.m, (p.flags & ADJ_REDUCE_TB) != 0);
   const size_t sb = (size_t)L.stride * sizeof(R);
 #define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) return do_launch(adjoint_out_kernel<R, N_, M_, (G_ > 32 ? 128 : G_)>, p, (G_ > 32 ? 128 : G_), sb, p.B, st, nl);
   DMPC_SHAPES(X)
@@ -149,6 +149,15 @@ int launch_adjoint_out(const AdjOutParams<R>& p, cudaStream_t st, long long* nl)
   }
 }
 
+template <typename R>
+int launch_reduce_partials(const R* red, int B, int rsz, R* out, cudaStream_t st, long long* nl) {
+  const int wpb = 4;
+  reduce_partials_kernel<R><<<(rsz + wpb - 1) / wpb, wpb * 32, 0, st>>>(red, B, rsz, out);
+  if (nl) ++*nl;
+  return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+}
+
+template int launch_reduce_partials<DMPC_REAL>(const DMPC_REAL*, int, int, DMPC_REAL*, cudaStream_t, long long*);
 template int launch_lqr_solve<DMPC_REAL>(const LqrParams<DMPC_REAL>&, cudaStream_t, long long*);
 template int launch_lqr_dtau<DMPC_REAL>(const DtauParams<DMPC_REAL>&, cudaStream_t, long long*);
 template int launch_adjoint_out<DMPC_REAL>(const AdjOutParams<DMPC_REAL>&, cudaStream_t, long long*);

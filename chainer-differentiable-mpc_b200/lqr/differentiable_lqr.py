@@ -114,6 +114,25 @@ class DiffLqr(FunctionNodeBase):
             df = d["df"].download(self._host_buf("df", (Tm, B, n)))[:T - 1]
         return dx0, dC, dc, dF, df
 
+    def backward_reduced_numpy(self, grad_x, grad_u):
+        """KKT adjoint with the (T,B)-sum fused in (dmpc_lqr_adjoint_reduced): returns
+        (dx0 [B,n], sum dC [s,s], sum dc [s], sum dF [n,s], sum df [n]) - what a shared-parameter model
+        (LqrNet, reference :186-198) receives after the backward of expand_time_batch - without materialising
+        the [T,B,...] gradients."""
+        T, B, n, m, s, dt = self.T, self.n_batch, self.n_state, self.n_ctrl, self.n_sc, self.dtype
+        d = self._buffers()
+        ctx = self._ctx
+        rsz = ctx.reduced_grad_elems(n, m)
+        if "partials" not in d:
+            d["partials"] = ctx.empty((B, rsz), dt); d["sums"] = ctx.empty((rsz,), dt)
+        d["gx"].upload(as_f(grad_x, dt)); d["gu"].upload(as_f(grad_u, dt))
+        ctx.lqr_adjoint_reduced(dt, T, B, n, m, d["C"], d["c"], d["F"], d["x"], d["u"], d["gx"], d["gu"], d["Ks"],
+                                d["fac"], d["dc"], d["partials"], d["dx0"], d["sums"],
+                                _native.ADJ_STRICT_REFERENCE if self.strict_reference else 0)
+        dx0 = d["dx0"].download(sync=False)
+        sums = d["sums"].download()
+        return (dx0,) + _native.Context.split_reduced(sums, n, m)
+
     # ---- Chainer FunctionNode protocol (reference :41-142) -----------------------------------
     def check_type_forward(self, in_types):
         pass

@@ -199,6 +199,30 @@ class MPCstep(FunctionNodeBase):
         self.active_index = act.download().astype(bool)
         return dx0.download(), dC.download(), dc.download(), dF.download(), (None if df is None else df.download())
 
+    def backward_reduced_numpy(self, dl_dx, dl_du):
+        """MPCstep.backward with the (T,B)-sum of dC, dc, dF, df fused in (dmpc_mpc_step_backward_reduced): returns
+        (dx0 [B,n], sum dC [s,s], sum dc [s], sum dF [n,s], sum df [n]) - the gradients IL_Env.mpc's repeated q, p
+        (env_dx/il_env.py:120-129) and MpcNet's A, B (mpc_net.py:78-86) receive."""
+        T, B, n, m, s = self.T, self.n_batch, self.n_state, self.n_ctrl, self.n_sc
+        ctx = self._ctx
+        x_init, C_hat, c_hat, F_hat, f_hat = self._fwd
+        C_hat = as_f(C_hat)
+        dt = C_hat.dtype
+        c_hat, F_hat = as_f(c_hat, dt), as_f(F_hat, dt)
+        new_x, new_u = as_f(self._out_xu[0], dt), as_f(self._out_xu[1], dt)
+        lo, hi = as_f(self.u_lower, dt), as_f(self.u_upper, dt)
+        gx = None if dl_dx is None else ctx.to_device(as_f(dl_dx, dt))
+        gu = None if dl_du is None else ctx.to_device(as_f(dl_du, dt))
+        rsz = ctx.reduced_grad_elems(n, m)
+        wsK = ctx.empty((T, B, m, n), dt); wsk = ctx.empty((T, B, m), dt); wsd = ctx.empty((T, B, s), dt)
+        act = ctx.empty((T, B, m), np.uint8)
+        part = ctx.empty((B, rsz), dt); sums = ctx.empty((rsz,), dt); dx0 = ctx.empty((B, n), dt)
+        ctx.mpc_step_backward_reduced(dt, T, B, n, m, ctx.to_device(C_hat), ctx.to_device(c_hat), ctx.to_device(F_hat),
+                                      F_hat.shape[0], ctx.to_device(new_x), ctx.to_device(new_u), ctx.to_device(lo),
+                                      ctx.to_device(hi), gx, gu, wsK, wsk, wsd, act, part, dx0, sums)
+        self.active_index = act.download().astype(bool)
+        return (dx0.download(),) + _native.Context.split_reduced(sums.download(), n, m)
+
     def backward(self, target_input_indexes, grad_outputs):
         dl_dx, dl_du = grad_outputs
         g = self.backward_numpy(to_xp(dl_dx), to_xp(dl_du))

@@ -239,6 +239,28 @@ int dmpc_boxddp_solve(dmpc_handle h, int dtype, int T, int B, int n, int m,
                       void* d_x_best, void* d_u_best, void* d_costs_best, void* d_du_best, void* d_du_last,
                       void* d_F_lin, void* d_f_lin, int* h_n_iter, int* h_status, int* h_flags, void* stream);
 
+/*
+ * Fused parameter-gradient reduction: the backward of util.expand_time_batch (util.py:361-377 - the
+ * sum over T and B that every shared-parameter model applies to dC, dc, dF, df: LqrNet differentiable_lqr.py:186-198,
+ * MpcNet mpc_net.py:78-86, IL_Env.mpc il_env.py:120-129) is done inside the adjoint kernel, so the [T,B,s,s] /
+ * [T,B,n,s] gradient tensors are never written.  Same arguments as dmpc_lqr_adjoint / dmpc_mpc_step_backward except:
+ *   d_ws_dtau[T,B,s] and d_ws_partials[B * dmpc_reduced_grad_elems(n,m)] are caller-owned workspaces;
+ *   d_sums[dmpc_reduced_grad_elems(n,m)] = (sum dC [s,s] | sum dc [s] | sum dF [n,s] | sum df [n]) over (t,b),
+ *   summed in a fixed order (deterministic); d_dx0[B,n] stays per element.
+ * The result feeds the NCCL all-reduce of the training step directly (a few hundred doubles per rank).
+ */
+size_t dmpc_reduced_grad_elems(int n, int m);
+int dmpc_lqr_adjoint_reduced(dmpc_handle h, int dtype, int T, int B, int n, int m,
+                             const void* d_C, const void* d_c, const void* d_F, const void* d_x, const void* d_u,
+                             const void* d_gx, const void* d_gu, const void* d_Ks, const void* d_fac,
+                             void* d_ws_dtau, void* d_ws_partials, void* d_dx0, void* d_sums, int flags, void* stream);
+int dmpc_mpc_step_backward_reduced(dmpc_handle h, int dtype, int T, int B, int n, int m,
+                                   const void* d_C, const void* d_c, const void* d_F, int F_T,
+                                   const void* d_x, const void* d_u, const void* d_lower, const void* d_upper,
+                                   const void* d_gx, const void* d_gu,
+                                   void* d_ws_Ks, void* d_ws_ks, void* d_ws_dtau, void* d_active,
+                                   void* d_ws_partials, void* d_dx0, void* d_sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
