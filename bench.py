@@ -250,15 +250,26 @@ def run_b200(args):
     # ---- kernel-level durations (serial, chunk 0, events on the launching stream) for the roofline.
     #      "forward" is the launch the timed step really makes (Riccati sweep + rollout fused); the factor-only
     #      and rollout-only launches are timed beside it to split it; "adjoint" = lqr_dtau_kernel + adjoint_out_kernel.
-    kt = {"forward": [], "factor": [], "rollout": [], "adjoint": []}
+    rsz = ctx.reduced_grad_elems(n, m)
+    red = dict(part=torch.empty(Bc, rsz, dtype=f64, device=dev), sums=torch.empty(rsz, dtype=f64, device=dev))
+
+    def bwd_reduced(i, stream):
+        pr, out = chunks[i]
+        ctx.lqr_adjoint_reduced(np.float64, T, Bc, n, m, P(pr["C"]), P(pr["c"]), P(pr["F"]), P(out["x"]), P(out["u"]),
+                                P(pr["gx"]), P(pr["gu"]), P(out["Ks"]), P(out["fac"]), P(out["dc"]), P(red["part"]),
+                                P(out["dx0"]), P(red["sums"]), _native.ADJ_STRICT_REFERENCE, stream.cuda_stream)
+
+    kt = {"forward": [], "factor": [], "rollout": [], "adjoint": [], "adjoint_reduced": []}
     for _ in range(3):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         e[0].record(sA)
         fwd(0, sA, FULL); e[1].record(sA)
         bwd(0, sA); e[2].record(sA)
         fwd(0, sA, _native.LQR_FACTOR | _native.LQR_SAVE_FAC); e[3].record(sA)
         fwd(0, sA, _native.LQR_ROLLOUT); e[4].record(sA)
+        bwd_reduced(0, sA); e[5].record(sA)
         torch.cuda.synchronize()
+        kt["adjoint_reduced"].append(e[4].elapsed_time(e[5]))
         kt["forward"].append(e[0].elapsed_time(e[1])); kt["adjoint"].append(e[1].elapsed_time(e[2]))
         kt["factor"].append(e[2].elapsed_time(e[3])); kt["rollout"].append(e[3].elapsed_time(e[4]))
     kt = {k: float(np.mean(v)) for k, v in kt.items()}
@@ -296,6 +307,9 @@ def run_b200(args):
                        "role": "Riccati sweep + rollout, one launch (factor-only %.3f ms, rollout-only %.3f ms)" % (kt["factor"], kt["rollout"])},
             "lqr_dtau_kernel+adjoint_out_kernel": {"ms": kt["adjoint"], "launches_per_step": 2,
                                                    "algorithmic_bytes": Bc * (tot_b - fwd_b), "role": "KKT adjoint"}}
+        extra_kernels = {"lqr_dtau_kernel+adjoint_out_kernel<REDUCE_TB>+reduce_partials_kernel": {
+            "ms": kt["adjoint_reduced"], "role": "KKT adjoint with the (T,B)-sum of dC,dc,dF,df fused in (shared-parameter "
+            "models; not part of the timed step, which materialises the full gradients as the reference does)"}}
         for name, k in kernels.items():
             k["achieved_gbs"] = k["algorithmic_bytes"] / (k["ms"] * 1e-3) / 1e9
             k["hbm_frac"] = k["achieved_gbs"] / peak
@@ -320,7 +334,8 @@ def run_b200(args):
             k = kernels[dom]
             roof = {"bound": "hbm", "kernel": dom, "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": k["hbm_frac"], "traffic": k["traffic"], "peak_source": peak_src}
-        roof.update({"hbm_peak_gbs": peak, "hbm_peak_source": peak_src, "kernels": kernels, "chunk_batch": Bc,
+        roof.update({"hbm_peak_gbs": peak, "hbm_peak_source": peak_src, "kernels": kernels, "other_kernels": extra_kernels,
+                     "chunk_batch": Bc,
                      "whole_step_achieved_gbs": whole, "whole_step_hbm_frac": whole / peak,
                      "algorithmic_bytes_per_solve": {"fwd": fwd_b, "fwd_bwd": tot_b},
                      "traffic_source": "ncu dram__bytes_read+write per solve x launch batch (profiles/r1/traffic.json)"})
@@ -337,19 +352,20 @@ def run_b200(args):
     #      gradient dF and all-reduce(sum) it over the ranks (NCCL); reported, not part of the solve metric
     exch = None
     if dist is not None:
-        _, out0 = chunks[0]
         ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True); ev2 = torch.cuda.Event(enable_timing=True)
         red_ms, ar_ms = [], []
         for _ in range(8):
-            ev0.record()
-            gF = out0["dF"].sum(dim=(0, 1))
-            ev1.record()
-            dist.all_reduce(gF, op=dist.ReduceOp.SUM)
+            ev0.record(sA)
+            bwd_reduced(0, sA)
+            ev1.record(sA)
+            torch.cuda.current_stream().wait_stream(sA)
+            ev1b = torch.cuda.Event(enable_timing=True); ev1b.record()
+            dist.all_reduce(red["sums"], op=dist.ReduceOp.SUM)
             ev2.record()
             torch.cuda.synchronize()
-            red_ms.append(ev0.elapsed_time(ev1)); ar_ms.append(ev1.elapsed_time(ev2))
-        exch = {"what": "sum_(t,b) dF -> [n,s] then NCCL all_reduce(sum) of %d doubles" % (n * s),
-                "local_reduce_ms": float(np.median(red_ms)), "allreduce_ms": float(np.median(ar_ms)), "world": world}
+            red_ms.append(ev0.elapsed_time(ev1)); ar_ms.append(ev1b.elapsed_time(ev2))
+        exch = {"what": "adjoint with fused (T,B)-sum -> %d doubles (dC|dc|dF|df), then NCCL all_reduce(sum)" % rsz,
+                "adjoint_reduced_ms": float(np.median(red_ms)), "allreduce_ms": float(np.median(ar_ms)), "world": world}
 
     # ---- e2e through the public API with host buffers (rank-local chunk) -----------------
     e2e = None
@@ -376,6 +392,10 @@ def run_b200(args):
                 line["mpc_step_throughput"] = mpc_step_throughput(ctx, torch, dev)
             except Exception as ex:
                 line["mpc_step_throughput"] = {"error": repr(ex)[:200]}
+            try:
+                line["il_iteration"] = il_iteration()
+            except Exception as ex:
+                line["il_iteration"] = {"error": repr(ex)[:200]}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -520,6 +540,53 @@ def mpc_step_latency(ctx, n_calls=200, cpu_calls=10, with_cpu=True):
                 ts.append(time.perf_counter() - t0)
         out["cpu_port_p50_ms"] = float(np.median(ts[2:])) * 1e3
     return out
+
+
+def il_iteration(B=8192, reps=3):
+    """BASELINE config 4 per-GPU shard: one imitation-learning iteration on the pendulum as env_dx/il_exp.py:249-275
+    wires it - BoxDDP forward (device-resident loop) through the facade with host arrays, then the backward of
+    loss = mean((u - u_expert)^2) through the final MPCstep with the (T,B)-sum fused in -> gradients of the repeated
+    q (diag of C) and p (c) of IL_Env.mpc (il_env.py:120-129)."""
+    import io
+    import contextlib
+    import warnings
+    from box_ddp import BoxDDP
+    from util import QuadCost
+    from pendulum_dx import PendulumDx
+    rs = np.random.RandomState(0)
+    th = rs.rand(B) * np.pi - np.pi / 2
+    x0 = np.stack((np.cos(th), np.sin(th), rs.rand(B) * 2 - 1), axis=1)
+    dx = PendulumDx()
+    qv, pv = dx.get_true_obj()
+    T = 20
+    q_learn = qv * (1.0 + 0.1 * rs.randn(4)) ; p_learn = pv + 0.05 * rs.randn(4)
+    Q = np.repeat(np.repeat(np.diag(q_learn)[None, None], T, 0), B, 1)
+    p = np.repeat(np.repeat(p_learn[None, None], T, 0), B, 1)
+    u_exp = np.clip(rs.randn(T, B, 1), -2, 2)
+    best = None
+    for _ in range(reps):
+        solver = BoxDDP(T=T, u_lower=dx.lower, u_upper=dx.upper, n_batch=B, n_state=3, n_ctrl=1, u_init=None,
+                        eps=dx.mpc_eps, max_iter=500, exit_unconverged=False, detach_unconverged=True,
+                        line_search_decay=dx.linesearch_decay, max_line_search_iter=dx.max_linesearch_iter,
+                        update_dynamics=False)
+        with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+            warnings.simplefilter("ignore")
+            t0 = time.perf_counter()
+            x, u, costs = solver((x0, QuadCost(Q, p), dx))
+            t1 = time.perf_counter()
+            un = np.asarray(getattr(u, "array", u))
+            gu = 2.0 * (un - u_exp) / un.size
+            g = solver.last_step.backward_reduced_numpy(None, gu)
+            t2 = time.perf_counter()
+        dq, dp = np.diag(g[1]).copy(), g[2]
+        cur = dict(fwd_ms=1e3 * (t1 - t0), bwd_ms=1e3 * (t2 - t1), n_iter=solver.info["n_iter"], status=solver.info["status"])
+        if best is None or cur["fwd_ms"] + cur["bwd_ms"] < best["fwd_ms"] + best["bwd_ms"]:
+            best = cur
+    best.update({"config": "c4 shard: pendulum n=3 m=1 T=20 B=%d, BoxDDP (device loop) + MPCstep backward with fused (T,B)-sum, "
+                           "host numpy in/out" % B,
+                 "mpc_solves_per_sec": B / ((best["fwd_ms"] + best["bwd_ms"]) * 1e-3), "grad_q_finite": bool(np.isfinite(dq).all()),
+                 "grad_p_finite": bool(np.isfinite(dp).all())})
+    return best
 
 
 def mpc_step_throughput(ctx, torch, dev, B=16384, reps=5):

@@ -460,7 +460,7 @@ __host__ __device__ inline AdjLayout adj_layout(int n, int m, bool reduce = fals
   return L;
 }
 
-template <typename R, int N, int M, int G>
+template <typename R, int N, int M, int G, bool RED = false>
 __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = N > 0 ? N : p.n;
@@ -473,12 +473,27 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
   int e = blockIdx.x * epb + eloc;
   const bool valid = e < B;
   if (!valid) e = B - 1;
-  const bool reduce = (p.flags & ADJ_REDUCE_TB) != 0;
-  const AdjLayout L = adj_layout<R>(n, m, reduce);
+  constexpr bool reduce = RED;                 // ADJ_REDUCE_TB is a separate instantiation (register budget)
+  const AdjLayout L = adj_layout<R>(n, m, reduce && N == 0);
   R* sm = reinterpret_cast<R*>(smem_raw) + (size_t)eloc * L.stride;
   R* lam = sm + L.lam; R* dlam = sm + L.dlam; R* lamn = sm + L.lamn; R* dlamn = sm + L.dlamn;
+  // ADJ_REDUCE_TB accumulators: every output (i,j) is owned by one lane for the whole horizon, so compile-time
+  // shapes keep the running sums in registers (acc*[k] <-> o = lane + k G); runtime shapes keep them in shared memory
+  constexpr bool REG = RED && N > 0;
+  constexpr int S_ = N + M;
+  constexpr int KC = REG ? (S_ * S_ + G - 1) / G : 1, KF = REG ? (N * S_ + G - 1) / G : 1,
+                Kc = REG ? (S_ + G - 1) / G : 1, Kf = REG ? (N + G - 1) / G : 1;
+  R accC[KC], accF[KF], accc[Kc], accf[Kf];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) accC[k] = R(0);
+#pragma unroll
+  for (int k = 0; k < KF; ++k) accF[k] = R(0);
+#pragma unroll
+  for (int k = 0; k < Kc; ++k) accc[k] = R(0);
+#pragma unroll
+  for (int k = 0; k < Kf; ++k) accf[k] = R(0);
   R* rC = sm + L.red; R* rc = rC + s * s; R* rF = rc + s; R* rf = rF + n * s;     // per-element sums over t
-  if (reduce) for (int o = g.lane; o < adj_red_elems(n, m); o += G) rC[o] = R(0);
+  if (reduce && !REG) for (int o = g.lane; o < adj_red_elems(n, m); o += G) rC[o] = R(0);
   const size_t tb = (size_t)B;
   const int nxoff = rup(n, 16 / (int)sizeof(R));
   const bool neg = (p.flags & ADJ_NEGATE) != 0;
@@ -511,13 +526,18 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
     // dF_t = dlam_{t+1} (x) tau_t + lam_{t+1} (x) dtau_t      (t < T-1)
     if (t < T - 1 && valid) {
       R* dFg = p.dF + idx * n * s;
-      for (int o = g.lane; o < n * s; o += G) {
-        const int i = o / s, j = o - i * s;
-        const R v = sgn * (dlam[i] * tau(j) + lam[i] * dt[j]);
-        if (reduce) rF[o] += v; else dFg[o] = v;
+      auto dF_val = [&](int o) -> R { const int i = o / s, j = o - i * s; return sgn * (dlam[i] * tau(j) + lam[i] * dt[j]); };
+      if (reduce && REG) {
+#pragma unroll
+        for (int k = 0; k < KF; ++k) { const int o = g.lane + k * G; if (o < n * s) accF[k] += dF_val(o); }
+      } else {
+        for (int o = g.lane; o < n * s; o += G) { const R v = dF_val(o); if (reduce) rF[o] += v; else dFg[o] = v; }
       }
       if (!(p.flags & ADJ_QUIRK_DF)) {
-        if (reduce) { for (int o = g.lane; o < n; o += G) rf[o] += sgn * dlam[o]; }
+        if (reduce && REG) {
+#pragma unroll
+          for (int k = 0; k < Kf; ++k) { const int o = g.lane + k * G; if (o < n) accf[k] += sgn * dlam[o]; }
+        } else if (reduce) { for (int o = g.lane; o < n; o += G) rf[o] += sgn * dlam[o]; }
         else if (p.df) { for (int o = g.lane; o < n; o += G) p.df[idx * n + o] = sgn * dlam[o]; }
       }
     }
@@ -537,20 +557,30 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
     if (valid) {
       R* dCg = p.dC + idx * s * s;
       const bool quirk = (p.flags & ADJ_QUIRK_DC) != 0;
-      for (int o = g.lane; o < s * s; o += G) {
+      auto dC_val = [&](int o) -> R {
         const int i = o / s, j = o - i * s;
         const R a = dt[i] * tau(j), b = tau(i) * dt[j];
-        const R v = quirk ? (R(0.5) * a + b) : (sgn * R(0.5) * (a + b));
-        if (reduce) rC[o] += v; else dCg[o] = v;
+        return quirk ? (R(0.5) * a + b) : (sgn * R(0.5) * (a + b));
+      };
+      if (reduce && REG) {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) { const int o = g.lane + k * G; if (o < s * s) accC[k] += dC_val(o); }
+#pragma unroll
+        for (int k = 0; k < Kc; ++k) { const int o = g.lane + k * G; if (o < s) accc[k] += sgn * dt[o]; }
+      } else {
+        for (int o = g.lane; o < s * s; o += G) { const R v = dC_val(o); if (reduce) rC[o] += v; else dCg[o] = v; }
       }
-      if (reduce) { for (int o = g.lane; o < s; o += G) rc[o] += sgn * dt[o]; }
+      if (reduce) { if (!REG) for (int o = g.lane; o < s; o += G) rc[o] += sgn * dt[o]; }
       else if (neg || p.dc != p.dtau) for (int o = g.lane; o < s; o += G) p.dc[idx * s + o] = sgn * dt[o];
     }
     g.sync();
     for (int o = g.lane; o < n; o += G) { lam[o] = lamn[o]; dlam[o] = dlamn[o]; }
     if (valid) {
       if ((p.flags & ADJ_QUIRK_DF) && t < T - 1) {
-        if (reduce) { for (int o = g.lane; o < n; o += G) rf[o] += sgn * dlamn[o]; }
+        if (reduce && REG) {
+#pragma unroll
+          for (int k = 0; k < Kf; ++k) { const int o = g.lane + k * G; if (o < n) accf[k] += sgn * dlamn[o]; }
+        } else if (reduce) { for (int o = g.lane; o < n; o += G) rf[o] += sgn * dlamn[o]; }
         else if (p.df) { for (int o = g.lane; o < n; o += G) p.df[idx * n + o] = sgn * dlamn[o]; }
       }
       if (t == 0) for (int o = g.lane; o < n; o += G) p.dx0[(size_t)e * n + o] = sgn * dlamn[o];
@@ -562,7 +592,18 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
     if (valid) {
       const int rsz = adj_red_elems(n, m);
       R* out = p.red + (size_t)e * rsz;
-      for (int o = g.lane; o < rsz; o += G) out[o] = rC[o];
+      if (REG) {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) { const int o = g.lane + k * G; if (o < s * s) out[o] = accC[k]; }
+#pragma unroll
+        for (int k = 0; k < Kc; ++k) { const int o = g.lane + k * G; if (o < s) out[s * s + o] = accc[k]; }
+#pragma unroll
+        for (int k = 0; k < KF; ++k) { const int o = g.lane + k * G; if (o < n * s) out[s * s + s + o] = accF[k]; }
+#pragma unroll
+        for (int k = 0; k < Kf; ++k) { const int o = g.lane + k * G; if (o < n) out[s * s + s + n * s + o] = accf[k]; }
+      } else {
+        for (int o = g.lane; o < rsz; o += G) out[o] = rC[o];
+      }
     }
     return;
   }

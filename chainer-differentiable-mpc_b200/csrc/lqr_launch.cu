@@ -136,17 +136,23 @@ int launch_lqr_dtau(const DtauParams<R>& p, cudaStream_t st, long long* nl) {
 template <typename R>
 int launch_adjoint_out(const AdjOutParams<R>& p, cudaStream_t st, long long* nl) {
   const ShapeInfo si = pick_shape_impl(p.n, p.m);
-  const AdjLayout L = adj_layout<R>(p.n, p.m, (p.flags & ADJ_REDUCE_TB) != 0);
+  const bool red = (p.flags & ADJ_REDUCE_TB) != 0;
+  const AdjLayout L = adj_layout<R>(p.n, p.m, red && !si.specialised);
   const size_t sb = (size_t)L.stride * sizeof(R);
-#define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) return do_launch(adjoint_out_kernel<R, N_, M_, (G_ > 32 ? 128 : G_)>, p, (G_ > 32 ? 128 : G_), sb, p.B, st, nl);
+#define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) \
+    return red ? do_launch(adjoint_out_kernel<R, N_, M_, (G_ > 32 ? 128 : G_), true>, p, (G_ > 32 ? 128 : G_), sb, p.B, st, nl) \
+               : do_launch(adjoint_out_kernel<R, N_, M_, (G_ > 32 ? 128 : G_), false>, p, (G_ > 32 ? 128 : G_), sb, p.B, st, nl);
   DMPC_SHAPES(X)
 #undef X
+#define Y(G_) return red ? do_launch(adjoint_out_kernel<R, 0, 0, G_, true>, p, G_, sb, p.B, st, nl) \
+                         : do_launch(adjoint_out_kernel<R, 0, 0, G_, false>, p, G_, sb, p.B, st, nl);
   switch (si.G) {
-    case 8: return do_launch(adjoint_out_kernel<R, 0, 0, 8>, p, 8, sb, p.B, st, nl);
-    case 16: return do_launch(adjoint_out_kernel<R, 0, 0, 16>, p, 16, sb, p.B, st, nl);
-    case 32: return do_launch(adjoint_out_kernel<R, 0, 0, 32>, p, 32, sb, p.B, st, nl);
-    default: return do_launch(adjoint_out_kernel<R, 0, 0, 128>, p, 128, sb, p.B, st, nl);
+    case 8: Y(8)
+    case 16: Y(16)
+    case 32: Y(32)
+    default: Y(128)
   }
+#undef Y
 }
 
 template <typename R>
