@@ -94,9 +94,6 @@ struct WarpCfg {
                 Oqu % 2 == 0 && Okk % 2 == 0 && RSTG % 2 == 0 && Rf % 2 == 0 && RK % 2 == 0 && Rk % 2 == 0, "16-byte alignment");
 };
 
-__device__ __forceinline__ void l2_prefetch_bulk(const void* g, unsigned bytes) {   // bytes % 16 == 0, g 16-byte aligned
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(g), "r"(bytes) : "memory");
-}
 
 // ---- bulk asynchronous copies (async proxy, completion on an mbarrier): one instruction moves a whole row /
 //      row block, so staging costs neither address registers nor issue slots
@@ -160,10 +157,11 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
     double* Qux_s = sm + Cfg::OQux; double* Quu_s = sm + Cfg::OQuu; double* Qi_s = sm + Cfg::OQi;
     double* K_s = sm + Cfg::OK; double* qu_s = sm + Cfg::Oqu; double* kk_s = sm + Cfg::Okk; double* mv_s = sm + Cfg::Omv;
 
-    // Single-buffered, refilled just in time by bulk copies: a row block of C_{t-1} is requested as soon as pass i
-    // of step t has read its accumulators (a full step ahead of its use); F_{t-1} (one padded row per lane),
-    // f_{t-1}, c_{t-1} are requested after the last Q pass and land behind the gain computation - from L2, where
-    // a bulk prefetch issued one step earlier put them.
+    // Single-buffered, refilled just in time: a row block of C_{t-1} is requested (bulk copy) as soon as pass i of
+    // step t has read its accumulators, a full step ahead of its use; F_{t-1} (padded rows, cp.async), f_{t-1},
+    // c_{t-1} are requested after the last Q pass and land behind the gain computation.  (An L2 bulk prefetch one
+    // step ahead was measured and removed: the prefetched lines did not survive until their use and were read
+    // twice from DRAM - +0.77 MB per solve, 6 % slower, profiles/r1/l2_prefetch_ab.txt.)
     unsigned long long* barF = bars;
     unsigned long long* barC = bars + 1;
     auto stage_C_rows = [&](int t, int i) {            // lane 0 only
@@ -196,14 +194,12 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
       mbar_arrive_expect_tx(barF, S * 8);
       bulk_g2s(cs, p.c + ((size_t)(T - 1) * tb + e) * S, S * 8, barF);
     }
-    if (T > 1 && lane == 0) l2_prefetch_bulk(p.F + ((size_t)(T - 2) * tb + e) * (N * S), N * S * 8);
 
     for (int t = T - 1; t >= 0; --t) {
       cp_async_wait<0>();
       mbar_wait(barF, par0); par0 ^= 1;
       mbar_wait(barC, par1); par1 ^= 1;
       __syncwarp();                                    // C_t, F_t, f_t, c_t are resident
-      if (t > 1 && lane == 0) l2_prefetch_bulk(p.F + ((size_t)(t - 2) * tb + e) * (N * S), N * S * 8);
       const size_t idx = (size_t)t * tb + e;
       const bool last = (t == T - 1);
 
@@ -367,10 +363,11 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
     }
   }
 
-  // ---- rollout (lqr_recursion.py:160-200): the warp re-streams K_t, k_t, F_t, f_t through two stages; an L2 bulk
-  //      prefetch four steps ahead keeps the (short) steps from waiting on DRAM
+  // ---- rollout (lqr_recursion.py:160-200): the warp re-streams K_t, k_t, F_t, f_t through two cp.async stages.  The
+  //      steps are short, so this phase is latency/HBM bound (10 KB per step); other warps of the SM are in their
+  //      DMMA-bound Riccati sweep meanwhile
   if (p.flags & LQR_DO_ROLLOUT) {
-    constexpr int LDKR = Cfg::LDKR, PD = 4;
+    constexpr int LDKR = Cfg::LDKR;
     __threadfence_block();
     __syncwarp();                                  // K_t, k_t written above by other lanes of this warp
     double* xs = sm + Cfg::Oxs;                    // [x; u]
@@ -391,8 +388,6 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
       if (hasF && have_f && lane >= 16) cp_async16(base + Cfg::Rf + (lane - 16) * 2, p.f + idx * N + (lane - 16) * 2);
       cp_async_commit();
     };
-    if (lane < PD && lane + 1 < T - 1) l2_prefetch_bulk(p.F + ((size_t)(lane + 1) * tb + e) * (N * S), N * S * 8);
-    if (lane >= 8 && lane < 8 + PD && lane - 7 < T) l2_prefetch_bulk(p.Ks + ((size_t)(lane - 7) * tb + e) * (M * N), M * N * 8);
     load_roll(0, 0);
     xs[lane] = p.x0[(size_t)e * N + lane];
     int st = 0;
@@ -400,8 +395,6 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
       cp_async_wait<0>();
       __syncwarp();
       if (t + 1 < T) load_roll(t + 1, st ^ 1);
-      if (lane == 0 && t + 1 + PD < T - 1) l2_prefetch_bulk(p.F + ((size_t)(t + 1 + PD) * tb + e) * (N * S), N * S * 8);
-      if (lane == 1 && t + 1 + PD < T) l2_prefetch_bulk(p.Ks + ((size_t)(t + 1 + PD) * tb + e) * (M * N), M * N * 8);
       const double* Fs = sm + st * Cfg::RSTG + Cfg::RF;
       const double* fs = sm + st * Cfg::RSTG + Cfg::Rf;
       const double* Kt = sm + st * Cfg::RSTG + Cfg::RK;
