@@ -44,17 +44,30 @@ __device__ __forceinline__ double quad_sum(double a) {      // sum over the 4 la
 
 // One pivot step of the Gauss-Jordan inverse (see warp_gj_inverse in lqr_dmma.cuh), branch-free so that the
 // compiler can interleave it with the independent DMMA stream of the Q passes.
+// 1/x to ~1 ulp: MUFU seed (20 bits), one Newton step (40 bits), one correction in residual form
+__device__ __forceinline__ double fast_rcp2(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = r * __fma_rn(-x, r, 2.0);
+  return __fma_rn(r, __fma_rn(-x, r, 1.0), r);
+}
+
 template <int M>
 __device__ __forceinline__ void gj_step(double (&c)[M], const int k) {
   constexpr unsigned FULL = 0xffffffffu;
   double pc[M];
 #pragma unroll
   for (int i = 0; i < M; ++i) pc[i] = __shfl_sync(FULL, c[i], k);
-  int piv = k;
-  unsigned best = abs_hi(pc[k]);
+  // argmax_{i >= k} |pc[i]| as a max-tree over keys (leading 28 bits of |x|) << 3 | (7 - i): ties (and magnitudes
+  // equal to 2^-17 relative) resolve to the smallest row, as in the sequential scan
+  unsigned key[M];
 #pragma unroll
-  for (int i = 0; i < M; ++i)
-    if (i > k) { const unsigned a = abs_hi(pc[i]); const bool g = a > best; best = g ? a : best; piv = g ? i : piv; }
+  for (int i = 0; i < M; ++i) key[i] = (i >= k) ? ((abs_hi(pc[i]) & ~7u) | (unsigned)(M - 1 - i)) : 0u;
+#pragma unroll
+  for (int w = 1; w < M; w <<= 1)
+#pragma unroll
+    for (int i = 0; i + w < M; i += 2 * w) key[i] = max(key[i], key[i + w]);
+  const int piv = (k == M - 1) ? k : (M - 1 - (int)(key[0] & 7u));
   double ck = c[k], pk = pc[k];
 #pragma unroll
   for (int i = 0; i < M; ++i)
@@ -63,7 +76,7 @@ __device__ __forceinline__ void gj_step(double (&c)[M], const int k) {
       ck = sw ? c[i] : ck; pk = sw ? pc[i] : pk;
       c[i] = sw ? c[k] : c[i]; pc[i] = sw ? pc[k] : pc[i];
     }
-  const double rp = fast_rcp(pk);
+  const double rp = fast_rcp2(pk);
   ck *= rp;
   c[k] = ck;
 #pragma unroll
