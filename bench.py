@@ -144,6 +144,30 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa(torch, local):
+    """Pin this rank's host threads (and therefore its pinned staging buffers, first-touch) to the CPUs NVML reports
+    as local to its GPU, so that the e2e feed does not cross sockets.  Best effort: any failure leaves affinity alone."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local)
+        h = None
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [i * 64 + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 # ------------------------------------------------------------------------------------- GPU arm
 def make_problem_torch(torch, dev, n, m, T, B, seed):
     """Synthetic random-stable dynamics, distinct per batch element."""
@@ -182,6 +206,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    n_local_cpus = bind_to_gpu_numa(torch, local)
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -469,7 +494,7 @@ def run_e2e(args, torch, ctx, n, m, T, world, dist, dev, rank):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
     return {"value": world * W * Be * reps / dt, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "batch_per_call": Be, "host_workers": W,
+            "batch_per_call": Be, "host_workers": W, "cpus_bound_to_gpu_numa_node": len(os.sched_getaffinity(0)),
             "api": "DiffLqr.apply_numpy + backward_numpy (pinned host buffers, %d host worker threads)" % W}
 
 
