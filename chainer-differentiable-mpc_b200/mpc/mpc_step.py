@@ -116,34 +116,55 @@ class MPCstep(FunctionNodeBase):
         if not isinstance(self.true_cost, QuadCost):
             raise NotImplementedError("true_cost must be a util.QuadCost (callable costs cannot run in the fused kernel)")
         tC, tc = as_f(self.true_cost.C, dt), as_f(self.true_cost.c, dt)
-        dC, dc, dF = ctx.to_device(C_hat), ctx.to_device(c_hat), ctx.to_device(F_hat)
-        df = None if (f_hat is None or self.need_expand) else ctx.to_device(f_hat[:T - 1])
-        dtC = dC if tC is C_hat or np.shares_memory(tC, C_hat) else ctx.to_device(tC)
-        dtc = dc if tc is c_hat or np.shares_memory(tc, c_hat) else ctx.to_device(tc)
+        # host -> device: every input that is not an alias of another one; small problems go through ONE packed copy
+        ins = {"C": C_hat, "c": c_hat, "F": F_hat, "x_nom": x_nom, "u_nom": u_nom, "lo": lo, "hi": hi}
+        if not (f_hat is None or self.need_expand):
+            ins["f"] = f_hat[:T - 1]
+        if not (tC is C_hat or np.shares_memory(tC, C_hat)):
+            ins["tC"] = tC
+        if not (tc is c_hat or np.shares_memory(tc, c_hat)):
+            ins["tc"] = tc
         if isinstance(self.true_dynamics, LinDx):
             dyn, params = _native.DYN_LINEAR, None
             tF = as_f(self.true_dynamics.F, dt)
             tf = None if to_xp(self.true_dynamics.f) is None else as_f(self.true_dynamics.f, dt)
-            dtF = dF if np.shares_memory(tF, F_hat) else ctx.to_device(tF)
-            dtf = None if tf is None else ctx.to_device(tf)
+            if not np.shares_memory(tF, F_hat):
+                ins["tF"] = tF
+            if tf is not None:
+                ins["tf"] = tf
         elif is_pendulum(self.true_dynamics):
             dyn, params = _native.DYN_PENDULUM, pendulum_params(self.true_dynamics)
-            dtF = dtf = None
+            tf = None
         else:
             raise NotImplementedError("true_dynamics must be util.LinDx or a PendulumDx (SURVEY.md H3)")
+        out_specs = [("x", (T, B, n), dt), ("u", (T, B, m), dt), ("Ks", (T, B, m, n), dt), ("ks", (T, B, m), dt),
+                     ("u_first", (T, B, m), dt), ("objs", (T, B), dt), ("costs", (B,), dt), ("old", (B,), dt),
+                     ("alphas", (B,), dt), ("n_qp", (T, B), np.int32), ("free", (T, B, m), np.uint8),
+                     ("n_ls", (B,), np.int32), ("flags", (B,), np.int32)]
+        packed = sum(a.nbytes for a in ins.values()) <= _native.PACK_LIMIT_BYTES
+        if packed:
+            pin = _native.PackedBuffers(ctx, [(k, a.shape, dt) for k, a in ins.items()])
+            d = pin.upload(ins)
+            pout = _native.PackedBuffers(ctx, out_specs)
+            o = pout.views
+        else:
+            d = {k: ctx.to_device(a) for k, a in ins.items()}
+            o = {k: ctx.empty(shape, t) for k, shape, t in out_specs}
+        dtC, dtc = d.get("tC", d["C"]), d.get("tc", d["c"])
+        dtF = d.get("tF", d["F"]) if dyn == _native.DYN_LINEAR else None
+        dtf = d.get("tf") if dyn == _native.DYN_LINEAR else None
         coupling = resolve_coupling(self.coupling, B, n, m)
-        o = dict(x=ctx.empty((T, B, n), dt), u=ctx.empty((T, B, m), dt), Ks=ctx.empty((T, B, m, n), dt),
-                 ks=ctx.empty((T, B, m), dt), u_first=ctx.empty((T, B, m), dt), objs=ctx.empty((T, B), dt),
-                 costs=ctx.empty((B,), dt), old=ctx.empty((B,), dt), alphas=ctx.empty((B,), dt),
-                 n_qp=ctx.empty((T, B), np.int32), free=ctx.empty((T, B, m), np.uint8),
-                 n_ls=ctx.empty((B,), np.int32), flags=ctx.empty((B,), np.int32))
-        ctx.mpc_step_forward(dt, T, B, n, m, dC, dc, dF, F_hat.shape[0], df, ctx.to_device(x_nom), ctx.to_device(u_nom),
-                             ctx.to_device(lo), ctx.to_device(hi), dtC, dtc, dyn, dtF, dtf, params, self.ls_decay,
+        ctx.mpc_step_forward(dt, T, B, n, m, d["C"], d["c"], d["F"], F_hat.shape[0], d.get("f"), d["x_nom"], d["u_nom"],
+                             d["lo"], d["hi"], dtC, dtc, dyn, dtF, dtf, params, self.ls_decay,
                              MAX_LS_TRIALS, self.need_expand,
                              _native.COUPLING_BATCH if coupling == "batch" else _native.COUPLING_ELEMENT,
                              o["x"], o["u"], o["Ks"], o["ks"], o["u_first"], o["objs"], o["costs"], o["old"],
                              o["alphas"], o["n_qp"], o["free"], o["n_ls"], o["flags"])
-        r = {k: v.download() for k, v in o.items()}
+        if packed:
+            r = pout.download()
+            pin.free(); pout.free()
+        else:
+            r = {k: v.download() for k, v in o.items()}
         flags = r["flags"]
         if (flags & _native.FLAG_QP_NOT_CONVERGED).any():
             warnings.warn("Projected Newton Quadratic Programming warning: Did not converge")
