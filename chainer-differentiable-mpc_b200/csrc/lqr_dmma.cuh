@@ -1,4 +1,6 @@
-// Large-state Riccati sweep on the FP64 tensor path (DMMA, mma.sync.m8n8k4.f64) for sm_100a.
+// Large-state Riccati sweep on the FP64 tensor path (DMMA, mma.sync.m8n8k4.f64) for sm_100a - FIRST GENERATION
+// (one CTA per element, operands in shared memory).  The default path is lqr_dmma_warp.cuh; this kernel is kept for
+// A/B runs (DMPC_DMMA_CTA=1) and provides the helpers both share (dmma884, fast_rcp, warp_gj_inverse, abs_hi).
 //
 // BASELINE config 5 (n=32, m=8, T=100): F^T V F is a real dense contraction (73 % of the flops), so it runs
 // on DMMA; tcgen05 has no f64 kind.  One CTA of four warps owns one batch element for the

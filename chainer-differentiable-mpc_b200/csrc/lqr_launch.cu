@@ -24,8 +24,6 @@ inline ShapeInfo pick_shape_impl(int n, int m) {
   return ShapeInfo{n, m, G, false};
 }
 
-template <int G> struct Tpb { static constexpr int value = (G <= 32) ? 128 : G; };
-
 template <typename K, typename P>
 static int do_launch(K kernel, const P& p, int G, size_t stride_bytes, int B, cudaStream_t st, long long* nl) {
   int tpb = (G <= 32) ? 128 : G;
@@ -168,6 +166,4 @@ template int launch_lqr_solve<DMPC_REAL>(const LqrParams<DMPC_REAL>&, cudaStream
 template int launch_lqr_dtau<DMPC_REAL>(const DtauParams<DMPC_REAL>&, cudaStream_t, long long*);
 template int launch_adjoint_out<DMPC_REAL>(const AdjOutParams<DMPC_REAL>&, cudaStream_t, long long*);
 
-#ifdef DMPC_DEFINE_PICK_SHAPE
-#endif
 }  // namespace dmpc
