@@ -137,3 +137,17 @@ def test_linearity_property_full_size(ctx):
     for k in ("x", "u"):
         mix = a * r1[k].download() + (1 - a) * r2[k].download()
         assert rel_err(r3[k].download(), mix) < 1e-9
+
+
+@pytest.mark.parametrize("T,B,with_f,sym", [(1, 3, True, True), (2, 6, True, True), (3, 1, False, True), (7, 9, False, False),
+                                           (16, 130, True, False)])
+def test_dmma_warp_kernel_edge_cases(ctx, T, B, with_f, sym):
+    """n=32, m=8 fp64 runs lqr_factor_dmma_warp_kernel (one warp per element, 4 per CTA): horizon edge cases, batch sizes
+    that leave warps of the last CTA idle, f=None, and a NON-symmetric C (the reference never symmetrises C, and the
+    kernel's operand re-use must not assume it)."""
+    n, m = 32, 8
+    pr = lqr_problem(T * 31 + B, T, B, n, m, with_f=with_f, sym=sym)
+    ox, ou, oK, ok = olqr.lqr_solve(pr["x0"], pr["C"], pr["c"], pr["F"], pr["f"], n, m)
+    r = run_solve(ctx, pr, np.float64)
+    assert rel_err(r["Ks"].download(), oK) < 1e-10 and rel_err(r["ks"].download(), ok) < 1e-10
+    assert rel_err(r["x"].download(), ox) < 1e-10 and rel_err(r["u"].download(), ou) < 1e-10
