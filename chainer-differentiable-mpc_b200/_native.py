@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libdiffmpc_b200.so")
 F64, F32 = 0, 1
 LQR_FACTOR, LQR_ROLLOUT, LQR_SAVE_FAC = 1, 2, 4
 ADJ_STRICT_REFERENCE = 1
+ADJ_STAGE_DTAU_ONLY, ADJ_STAGE_OUT_ONLY = 2, 4
 COUPLING_ELEMENT, COUPLING_BATCH = 0, 1
 DYN_LINEAR, DYN_PENDULUM = 0, 1
 FLAG_QP_NOT_CONVERGED, FLAG_NONFINITE, FLAG_LS_CAPPED = 1, 2, 4

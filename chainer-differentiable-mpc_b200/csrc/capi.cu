@@ -58,8 +58,12 @@ static int lqr_adjoint_impl(dmpc_handle h, int T, int B, int n, int m, const voi
   d.T = T; d.B = B; d.n = n; d.m = m;
   d.F = (const R*)F; d.gx = (const R*)gx; d.gu = (const R*)gu; d.Ks = (const R*)Ks; d.fac = (const R*)fac;
   d.dc = (R*)dc;
-  int rc = launch_lqr_dtau<R>(d, st, &h->launches);
-  if (rc) { h->err = "lqr_dtau launch failed"; return rc; }
+  int rc = DMPC_OK;
+  if (!(flags & DMPC_ADJ_STAGE_OUT_ONLY)) {
+    rc = launch_lqr_dtau<R>(d, st, &h->launches);
+    if (rc) { h->err = "lqr_dtau launch failed"; return rc; }
+  }
+  if (flags & DMPC_ADJ_STAGE_DTAU_ONLY) return rc;
   AdjOutParams<R> a;
   memset(&a, 0, sizeof(a));
   a.T = T; a.B = B; a.n = n; a.m = m; a.F_T = T - 1;

@@ -62,7 +62,11 @@ enum {
 
 /* adjoint flags */
 enum {
-  DMPC_ADJ_STRICT_REFERENCE = 1 /* reproduce differentiable_lqr.py:128 (dC precedence) and :133 (df shift) */
+  DMPC_ADJ_STRICT_REFERENCE = 1, /* reproduce differentiable_lqr.py:128 (dC precedence) and :133 (df shift) */
+  /* profiling aids: run one of the two kernels of dmpc_lqr_adjoint.  STAGE_OUT alone re-uses the d-tau that a
+   * previous full (or STAGE_DTAU) call left in d_dc, so the pair can be timed kernel by kernel. */
+  DMPC_ADJ_STAGE_DTAU_ONLY = 2,
+  DMPC_ADJ_STAGE_OUT_ONLY = 4
 };
 
 /* coupling of the batch-global control flow of PNQP */
