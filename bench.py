@@ -141,7 +141,7 @@ def run_reference(args):
             "config": {"workload": args.workload, "desc": desc, "n_state": n, "n_ctrl": m, "T": T, "batch_per_step": Bc},
             "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def bind_to_gpu_numa(torch, local):
@@ -211,8 +211,6 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     ctx = _native.Context(local)
     f64 = torch.float64
@@ -434,7 +432,7 @@ def run_b200(args):
                 line["il_iteration"] = il_iteration()
             except Exception as ex:
                 line["il_iteration"] = {"error": repr(ex)[:200]}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -676,7 +674,29 @@ def mpc_step_throughput(ctx, torch, dev, B=16384, reps=5):
             "flagged_elements": int((o["fl"] != 0).sum().item())}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Rank 0 prints exactly ONE JSON line on stdout.  Libraries write there too (NCCL's version banner, BoxDDP's
+    reference-faithful "Converged" prints), so file descriptor 1 is pointed at stderr for the whole run and the JSON
+    line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
