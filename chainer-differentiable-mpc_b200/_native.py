@@ -235,6 +235,7 @@ class Context:
             raise DiffMpcError("dmpc_create(device=%d) failed: %s" % (device, self.lib.dmpc_status_string(rc).decode()))
         self.h = h
         self.device = int(device)
+        self._pinned = []        # page-locked host allocations handed out by pinned_empty()
         self._pool = {}          # nbytes -> [device pointers]; avoids cudaMalloc/cudaFree per call
         self._pool_bytes = 0
         self.pool_limit = 8 << 30
@@ -278,11 +279,26 @@ class Context:
     def close(self):
         if self.h:
             self.trim()
+            for p in self._pinned:
+                self.lib.dmpc_host_free(self.h, p)
+            self._pinned = []
             self.lib.dmpc_destroy(self.h)
             self.h = None
 
     def sync(self, stream=None):
         self._check(self.lib.dmpc_sync(self.h, stream))
+
+    def pinned_empty(self, shape, dtype=np.float64):
+        """numpy array backed by page-locked host memory (dmpc_host_alloc): copies to / from it run at PCIe speed and
+        truly asynchronously.  The memory lives until the context is closed."""
+        dt = np.dtype(dtype)
+        shape = tuple(int(v) for v in shape)
+        nbytes = max(int(np.prod(shape, dtype=np.int64)) * dt.itemsize, 1)
+        p = _vp()
+        self._check(self.lib.dmpc_host_alloc(self.h, nbytes, ctypes.byref(p)))
+        self._pinned.append(p)
+        buf = (ctypes.c_ubyte * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
 
     @property
     def launches(self):

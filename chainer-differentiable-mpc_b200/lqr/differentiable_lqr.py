@@ -58,8 +58,7 @@ class DiffLqr(FunctionNodeBase):
             return np.empty(shape, self.dtype)
         a = self._host.get(name)
         if a is None or a.shape != tuple(shape):
-            import torch
-            a = torch.empty(tuple(shape), dtype=torch.float64 if self.dtype == np.float64 else torch.float32).pin_memory().numpy()
+            a = self._ctx.pinned_empty(shape, self.dtype)
             self._host[name] = a
         return a
 
