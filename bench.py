@@ -626,36 +626,50 @@ def il_iteration(B=8192, reps=3):
 
 
 def mpc_step_throughput(ctx, torch, dev, B=16384, reps=5):
-    """BASELINE config 3: box-constrained MPC step sweep n=8, m=4, T=50, B=16384, bounds tuned so that
-    roughly 30 % of the timesteps have a clamped control; device-resident, element coupling."""
+    """BASELINE config 3: box-constrained MPC step sweep n=8, m=4, T=50, B=16384, device-resident, element coupling.
+    The control bound is calibrated on a 2048-element sub-batch so that about 30 % of the timesteps end with a
+    clamped control; the achieved fraction of the full run is reported."""
     import _native
     T, n, m = 50, 8, 4
-    s = n + m
-    pr = make_problem_torch(torch, dev, n, m, T, B, seed=77)
     f64 = torch.float64
-    bound = 0.6
-    g = torch.Generator(device=dev); g.manual_seed(5)
-    u = torch.clamp(0.2 * torch.randn(T, B, m, dtype=f64, device=dev, generator=g), -bound, bound)
-    lo = torch.full((T, B, m), -bound, dtype=f64, device=dev); hi = -lo
-    x = torch.empty(T, B, n, dtype=f64, device=dev)
     P = lambda t: t.data_ptr()
     st = torch.cuda.Stream(device=dev)
-    torch.cuda.synchronize()
     sh = st.cuda_stream
-    ctx.get_traj(np.float64, T, B, n, m, _native.DYN_LINEAR, P(pr["x0"]), P(u), P(pr["F"]), P(pr["f"]), None, P(x), None, None, sh)
-    o = dict(x=torch.empty_like(x), u=torch.empty_like(u), Ks=torch.empty(T, B, m, n, dtype=f64, device=dev),
-             ks=torch.empty(T, B, m, dtype=f64, device=dev), uf=torch.empty_like(u), objs=torch.empty(T, B, dtype=f64, device=dev),
-             costs=torch.empty(B, dtype=f64, device=dev), old=torch.empty(B, dtype=f64, device=dev),
-             al=torch.empty(B, dtype=f64, device=dev), nqp=torch.empty(T, B, dtype=torch.int32, device=dev),
-             fr=torch.empty(T, B, m, dtype=torch.uint8, device=dev), nls=torch.empty(B, dtype=torch.int32, device=dev),
-             fl=torch.empty(B, dtype=torch.int32, device=dev))
 
-    def call():
-        ctx.mpc_step_forward(np.float64, T, B, n, m, P(pr["C"]), P(pr["c"]), P(pr["F"]), T - 1, P(pr["f"]), P(x), P(u),
-                             P(lo), P(hi), P(pr["C"]), P(pr["c"]), _native.DYN_LINEAR, P(pr["F"]), P(pr["f"]), None, 0.2, 64,
-                             True, _native.COUPLING_ELEMENT, P(o["x"]), P(o["u"]), P(o["Ks"]), P(o["ks"]), P(o["uf"]),
-                             P(o["objs"]), P(o["costs"]), P(o["old"]), P(o["al"]), P(o["nqp"]), P(o["fr"]), P(o["nls"]),
-                             P(o["fl"]), sh)
+    def setup(Bq, bound):
+        pr = make_problem_torch(torch, dev, n, m, T, Bq, seed=77)
+        g = torch.Generator(device=dev); g.manual_seed(5)
+        u = torch.clamp(0.2 * torch.randn(T, Bq, m, dtype=f64, device=dev, generator=g), -bound, bound)
+        lo = torch.full((T, Bq, m), -bound, dtype=f64, device=dev); hi = -lo
+        x = torch.empty(T, Bq, n, dtype=f64, device=dev)
+        torch.cuda.synchronize()
+        ctx.get_traj(np.float64, T, Bq, n, m, _native.DYN_LINEAR, P(pr["x0"]), P(u), P(pr["F"]), P(pr["f"]), None, P(x), None, None, sh)
+        o = dict(x=torch.empty_like(x), u=torch.empty_like(u), Ks=torch.empty(T, Bq, m, n, dtype=f64, device=dev),
+                 ks=torch.empty(T, Bq, m, dtype=f64, device=dev), uf=torch.empty_like(u), objs=torch.empty(T, Bq, dtype=f64, device=dev),
+                 costs=torch.empty(Bq, dtype=f64, device=dev), old=torch.empty(Bq, dtype=f64, device=dev),
+                 al=torch.empty(Bq, dtype=f64, device=dev), nqp=torch.empty(T, Bq, dtype=torch.int32, device=dev),
+                 fr=torch.empty(T, Bq, m, dtype=torch.uint8, device=dev), nls=torch.empty(Bq, dtype=torch.int32, device=dev),
+                 fl=torch.empty(Bq, dtype=torch.int32, device=dev))
+
+        def call():
+            ctx.mpc_step_forward(np.float64, T, Bq, n, m, P(pr["C"]), P(pr["c"]), P(pr["F"]), T - 1, P(pr["f"]), P(x), P(u),
+                                 P(lo), P(hi), P(pr["C"]), P(pr["c"]), _native.DYN_LINEAR, P(pr["F"]), P(pr["f"]), None, 0.2, 64,
+                                 True, _native.COUPLING_ELEMENT, P(o["x"]), P(o["u"]), P(o["Ks"]), P(o["ks"]), P(o["uf"]),
+                                 P(o["objs"]), P(o["costs"]), P(o["old"]), P(o["al"]), P(o["nqp"]), P(o["fr"]), P(o["nls"]),
+                                 P(o["fl"]), sh)
+
+        def clamped():
+            torch.cuda.synchronize()
+            return float(((o["u"] <= -bound + 1e-8) | (o["u"] >= bound - 1e-8)).any(dim=2).double().mean().item())
+        return call, clamped, o, (pr, u, lo, hi, x)
+
+    cal = {}
+    for b in (0.6, 0.8, 1.0, 1.2, 1.5):
+        call, clamped, _, keep = setup(2048, b)
+        call()
+        cal[b] = clamped()
+    bound = min(cal, key=lambda b: abs(cal[b] - 0.30))
+    call, clamped, o, keep = setup(B, bound)
     for _ in range(2):
         call()
     torch.cuda.synchronize()
@@ -666,9 +680,9 @@ def mpc_step_throughput(ctx, torch, dev, B=16384, reps=5):
     e1.record(st)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    clamped_steps = float(((o["u"] <= -bound + 1e-8) | (o["u"] >= bound - 1e-8)).any(dim=2).double().mean().item())
     return {"config": "c3 n=8 m=4 T=50 B=%d box-constrained MPC step (element coupling), bounds +-%.1f" % (B, bound),
-            "ms_per_step": ms, "mpc_steps_per_sec": B / (ms * 1e-3), "clamped_timestep_frac": clamped_steps,
+            "ms_per_step": ms, "mpc_steps_per_sec": B / (ms * 1e-3), "clamped_timestep_frac": clamped(),
+            "bound_calibration": {"%.1f" % b: round(v, 3) for b, v in cal.items()},
             "mean_qp_iters_per_timestep": float(o["nqp"].double().mean().item()),
             "mean_line_search_passes": float(o["nls"].double().mean().item()),
             "flagged_elements": int((o["fl"] != 0).sum().item())}
