@@ -481,8 +481,15 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
   // shapes keep the running sums in registers (acc*[k] <-> o = lane + k G); runtime shapes keep them in shared memory
   constexpr bool REG = RED && N > 0;
   constexpr int S_ = N + M;
-  constexpr int KC = REG ? (S_ * S_ + G - 1) / G : 1, KF = REG ? (N * S_ + G - 1) / G : 1,
+  // outer products in the REG path: lane = (row group ti, column tj); the lane keeps tau_j, dtau_j in registers and
+  // walks the rows ti, ti + NR, ... whose tau_i / dtau_i / lambda_i loads are warp broadcasts - two shared-memory
+  // loads per output instead of four and no index arithmetic
+  constexpr int NR = REG ? (G / S_ > 0 ? G / S_ : 1) : 1;
+  constexpr int KC = REG ? (S_ + NR - 1) / NR : 1, KF = REG ? (N + NR - 1) / NR : 1,
                 Kc = REG ? (S_ + G - 1) / G : 1, Kf = REG ? (N + G - 1) / G : 1;
+  static_assert(!REG || G >= S_, "REG path: one column per lane");
+  const int tj = REG ? g.lane % S_ : 0, ti = REG ? g.lane / S_ : 0;
+  const bool tile_lane = ti < NR;
   R accC[KC], accF[KF], accc[Kc], accf[Kf];
 #pragma unroll
   for (int k = 0; k < KC; ++k) accC[k] = R(0);
@@ -528,8 +535,11 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
       R* dFg = p.dF + idx * n * s;
       auto dF_val = [&](int o) -> R { const int i = o / s, j = o - i * s; return sgn * (dlam[i] * tau(j) + lam[i] * dt[j]); };
       if (reduce && REG) {
+        if (tile_lane) {
+          const R tau_j = tau(tj), dt_j = dt[tj];
 #pragma unroll
-        for (int k = 0; k < KF; ++k) { const int o = g.lane + k * G; if (o < n * s) accF[k] += dF_val(o); }
+          for (int k = 0; k < KF; ++k) { const int i = ti + k * NR; if (i < n) accF[k] += sgn * (dlam[i] * tau_j + lam[i] * dt_j); }
+        }
       } else {
         for (int o = g.lane; o < n * s; o += G) { const R v = dF_val(o); if (reduce) rF[o] += v; else dFg[o] = v; }
       }
@@ -563,8 +573,14 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
         return quirk ? (R(0.5) * a + b) : (sgn * R(0.5) * (a + b));
       };
       if (reduce && REG) {
+        if (tile_lane) {
+          const R tau_j = tau(tj), dt_j = dt[tj];
 #pragma unroll
-        for (int k = 0; k < KC; ++k) { const int o = g.lane + k * G; if (o < s * s) accC[k] += dC_val(o); }
+          for (int k = 0; k < KC; ++k) {
+            const int i = ti + k * NR;
+            if (i < s) { const R a = dt[i] * tau_j, b = tau(i) * dt_j; accC[k] += quirk ? (R(0.5) * a + b) : (sgn * R(0.5) * (a + b)); }
+          }
+        }
 #pragma unroll
         for (int k = 0; k < Kc; ++k) { const int o = g.lane + k * G; if (o < s) accc[k] += sgn * dt[o]; }
       } else {
@@ -593,12 +609,14 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
       const int rsz = adj_red_elems(n, m);
       R* out = p.red + (size_t)e * rsz;
       if (REG) {
+        if (tile_lane) {
 #pragma unroll
-        for (int k = 0; k < KC; ++k) { const int o = g.lane + k * G; if (o < s * s) out[o] = accC[k]; }
+          for (int k = 0; k < KC; ++k) { const int i = ti + k * NR; if (i < s) out[i * s + tj] = accC[k]; }
+#pragma unroll
+          for (int k = 0; k < KF; ++k) { const int i = ti + k * NR; if (i < n) out[s * s + s + i * s + tj] = accF[k]; }
+        }
 #pragma unroll
         for (int k = 0; k < Kc; ++k) { const int o = g.lane + k * G; if (o < s) out[s * s + o] = accc[k]; }
-#pragma unroll
-        for (int k = 0; k < KF; ++k) { const int o = g.lane + k * G; if (o < n * s) out[s * s + s + o] = accF[k]; }
 #pragma unroll
         for (int k = 0; k < Kf; ++k) { const int o = g.lane + k * G; if (o < n) out[s * s + s + n * s + o] = accf[k]; }
       } else {
