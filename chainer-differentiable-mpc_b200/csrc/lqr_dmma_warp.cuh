@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
         if (pi == 1) {
 #pragma unroll
           for (int ii = 0; ii < M; ++ii) cinv[ii] = (lane < M) ? Quu_s[ii * LDU + lane] : ((lane - M == ii) ? 1.0 : 0.0);
+          __syncwarp();                                // q_x (stored at the end of this pass) aliases the Quu panel
         }
         double qa = 0.0;
         if (!last) {
