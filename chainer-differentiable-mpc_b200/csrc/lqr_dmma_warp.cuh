@@ -275,6 +275,10 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
           acc[j][0] = c2.x; acc[j][1] = c2.y;
         }
         __syncwarp();
+        // Generic-proxy reads of this row block (the loads above, already consumed into registers) are ordered before
+        // the async-proxy refill by the warp barrier - the same read-then-release pattern as a TMA pipeline's consumer
+        // release; a fence.proxy.async here costs ~6 % of the kernel (it drains every outstanding memory operation)
+        // and is only required in the other direction (generic writes later read by the async proxy).
         if (t > 0 && lane == 0) {                      // refill this row block for the next step
           if (pi == 0) mbar_arrive_expect_tx(barC, S * S * 8);
           stage_C_rows(t - 1, i);
