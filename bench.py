@@ -306,6 +306,17 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # L2 policy (timing rules): the default workload streams 19.5 GB of inputs per step, far beyond the 126 MB L2.
+    # The small parity-shaped workloads (c2, c3s, c4s) would fit, so for them a 512 MB buffer is rewritten on the
+    # launching stream between timed steps and every step is timed by its own pair of events (flush excluded).
+    fwd_b_, tot_b_ = algorithmic_bytes(n, m, T)
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if B * tot_b_ < (1 << 30) else None
+
+    def flush_l2():
+        if flush_buf is not None:
+            with torch.cuda.stream(sA):
+                flush_buf.fill_(1)
+
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -324,6 +335,7 @@ def run_b200(args):
     kt = {"forward": [], "factor": [], "rollout": [], "adjoint": [], "adjoint_reduced": [], "dtau": [], "adjoint_out": []}
     for _ in range(3):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+        flush_l2()
         e[0].record(sA)
         fwd(0, sA, FULL); e[1].record(sA)
         bwd(0, sA); e[2].record(sA)
@@ -343,15 +355,27 @@ def run_b200(args):
     sampler.start()
     l0 = ctx.launches
     barrier()
-    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record(sA)
-    for _ in range(args.steps):
-        step()
-    t_end.record(sA)
-    barrier()
+    if flush_buf is None:
+        t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+        t_start.record(sA)
+        for _ in range(args.steps):
+            step()
+        t_end.record(sA)
+        barrier()
+        ms_total = t_start.elapsed_time(t_end)
+    else:
+        evs = []
+        for _ in range(args.steps):
+            flush_l2()
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(sA)
+            step()
+            b.record(sA)
+            evs.append((a, b))
+        barrier()
+        ms_total = sum(a.elapsed_time(b) for a, b in evs)
     launches = ctx.launches - l0
     clocks = sampler.stop()
-    ms_total = t_start.elapsed_time(t_end)
     if dist is not None:
         tt = torch.tensor([ms_total], dtype=f64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -420,7 +444,10 @@ def run_b200(args):
                 "config": {"workload": args.workload, "desc": desc, "n_state": n, "n_ctrl": m, "T": T,
                            "batch_per_gpu": B, "global_batch": B * world, "parallelism": "batch-sharded x%d" % world,
                            "chunks_per_gpu": K, "overlap": "fwd(chunk i+1) || bwd(chunk i) on two streams" if K > 1 else "none",
-                           "l2": "inputs (%.1f GB/GPU) larger than L2" % (B * fwd_b / 1e9), "finite_outputs": ok},
+                           "l2": ("inputs (%.1f GB/GPU) larger than L2" % (B * fwd_b / 1e9)) if flush_buf is None else
+                                 "512 MB flush buffer rewritten between timed steps (working set %.2f GB/GPU), each step "
+                                 "timed by its own event pair" % (B * tot_b / 1e9),
+                           "finite_outputs": ok},
                 "roofline": roof, "clocks": clocks, "gpu_launches": launches}
 
     # ---- the one exchange step of a training iteration: (T,B_local)-reduce the learned-dynamics

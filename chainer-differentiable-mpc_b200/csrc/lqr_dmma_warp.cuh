@@ -84,11 +84,25 @@ __device__ __forceinline__ void gj_step(double (&c)[M], const int k) {
     if (i != k) c[i] = __fma_rn(-pc[i], ck, c[i]);
 }
 
+// I/O element type of the kernel.  double: the tensors are fp64 in HBM.  float (the fp32 API): tensors are float in
+// HBM *and* in the staging buffers (half the traffic, half the staging bytes), widened to fp64 when a fragment is read;
+// the recursion itself runs on the same fp64 DMMA path, so the fp32 result is the correctly rounded fp64 one.
+template <typename IO> __device__ __forceinline__ double2 ld2(const IO* p);
+template <> __device__ __forceinline__ double2 ld2<double>(const double* p) { return *reinterpret_cast<const double2*>(p); }
+template <> __device__ __forceinline__ double2 ld2<float>(const float* p) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  return make_double2((double)v.x, (double)v.y);
+}
+__device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+__device__ __forceinline__ void st2(float* p, double a, double b) { *reinterpret_cast<float2*>(p) = make_float2((float)a, (float)b); }
+
 struct WarpCfg {
   static constexpr int N = 32, M = 8, S = 40;
   // F buffer: row pitch 42 doubles -> the four fragment rows 2t+e of a half-warp fall in distinct 32-byte
   // bank groups (4*LDF = 8 mod 32).  C buffer: dense (pitch 40), read as accumulator tiles (16 B per lane).
+  // float I/O: pitch 44 floats (16-byte aligned rows for cp.async; the rows 2t+e of a fragment read land 24 banks apart).
   static constexpr int LDF = 42;
+  template <typename IO> static constexpr int ldf() { return sizeof(IO) == 8 ? LDF : 44; }
   static constexpr int OF = 0, Of = OF + N * LDF, Oc = Of + N, OC = Oc + S, OSCR = OC + S * S;
   // per-warp scratch
   static constexpr int LDQ = 36;     // Qux panel [8][36]: B fragments by rows k0+t
@@ -135,18 +149,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 }
 // F_t ([32][40] contiguous in global memory) -> padded rows in shared memory: one row per cp.async instruction
 // (20 lanes x 16 bytes), so every address is base + compile-time immediate
-__device__ __forceinline__ void stage_F_rows(double* Fs, const double* Fg, int lane) {
-  if (lane < WarpCfg::S / 2) {
+template <typename IO>
+__device__ __forceinline__ void stage_F_rows(IO* Fs, const IO* Fg, int lane) {
+  constexpr int EP = 16 / sizeof(IO);              // elements per 16-byte chunk
+  if (lane < WarpCfg::S / EP) {
 #pragma unroll
-    for (int r = 0; r < WarpCfg::N; ++r) cp_async16(Fs + r * WarpCfg::LDF + lane * 2, Fg + r * WarpCfg::S + lane * 2);
+    for (int r = 0; r < WarpCfg::N; ++r) cp_async16(Fs + r * WarpCfg::ldf<IO>() + lane * EP, Fg + r * WarpCfg::S + lane * EP);
   }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
-template <int WPC>
-__global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel(LqrParams<double> p) {
+template <int WPC, typename IO>
+__global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel(LqrParams<IO> p) {
   using Cfg = WarpCfg;
-  constexpr int N = Cfg::N, M = Cfg::M, S = Cfg::S, LDF = Cfg::LDF, LDQ = Cfg::LDQ, LDU = Cfg::LDU, LDK = Cfg::LDK;
+  constexpr int N = Cfg::N, M = Cfg::M, S = Cfg::S, LDF = Cfg::ldf<IO>(), LDQ = Cfg::LDQ, LDU = Cfg::LDU, LDK = Cfg::LDK;
+  constexpr int W = sizeof(IO), EP = 16 / W;        // bytes per I/O element, elements per 16-byte chunk
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gr = lane >> 2, tg = lane & 3;
@@ -166,7 +183,8 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
   unsigned par0 = 0, par1 = 0;
 
   if (p.flags & LQR_DO_FACTOR) {
-    double* Fs = sm + Cfg::OF; double* fs = sm + Cfg::Of; double* cs = sm + Cfg::Oc; double* Cs = sm + Cfg::OC;
+    IO* Fs = reinterpret_cast<IO*>(sm + Cfg::OF); IO* fs = reinterpret_cast<IO*>(sm + Cfg::Of);
+    IO* cs = reinterpret_cast<IO*>(sm + Cfg::Oc); IO* Cs = reinterpret_cast<IO*>(sm + Cfg::OC);
     double* Qux_s = sm + Cfg::OQux; double* Quu_s = sm + Cfg::OQuu; double* Qi_s = sm + Cfg::OQi;
     double* K_s = sm + Cfg::OK; double* qu_s = sm + Cfg::Oqu; double* kk_s = sm + Cfg::Okk; double* mv_s = sm + Cfg::Omv;
 
@@ -178,16 +196,16 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
     unsigned long long* barF = bars;
     unsigned long long* barC = bars + 1;
     auto stage_C_rows = [&](int t, int i) {            // lane 0 only
-      bulk_g2s(Cs + i * 8 * S, p.C + ((size_t)t * tb + e) * (S * S) + i * 8 * S, 8 * S * 8, barC);
+      bulk_g2s(Cs + i * 8 * S, p.C + ((size_t)t * tb + e) * (S * S) + i * 8 * S, 8 * S * W, barC);
     };
     auto stage_Ffc = [&](int t) {                      // all lanes; t < T-1
       const size_t idx = (size_t)t * tb + e;
       stage_F_rows(Fs, p.F + idx * (N * S), lane);
       cp_async_commit();
       if (lane == 0) {
-        mbar_arrive_expect_tx(barF, (have_f ? N * 8 : 0) + S * 8);
-        bulk_g2s(cs, p.c + idx * S, S * 8, barF);
-        if (have_f) bulk_g2s(fs, p.f + idx * N, N * 8, barF);
+        mbar_arrive_expect_tx(barF, (have_f ? N * W : 0) + S * W);
+        bulk_g2s(cs, p.c + idx * S, S * W, barF);
+        if (have_f) bulk_g2s(fs, p.f + idx * N, N * W, barF);
       }
     };
 
@@ -202,10 +220,10 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
     }
 
     if (lane == 0) {                                   // step T-1 needs C and c only
-      mbar_arrive_expect_tx(barC, S * S * 8);
-      bulk_g2s(Cs, p.C + ((size_t)(T - 1) * tb + e) * (S * S), S * S * 8, barC);
-      mbar_arrive_expect_tx(barF, S * 8);
-      bulk_g2s(cs, p.c + ((size_t)(T - 1) * tb + e) * S, S * 8, barF);
+      mbar_arrive_expect_tx(barC, S * S * W);
+      bulk_g2s(Cs, p.C + ((size_t)(T - 1) * tb + e) * (S * S), S * S * W, barC);
+      mbar_arrive_expect_tx(barF, S * W);
+      bulk_g2s(cs, p.c + ((size_t)(T - 1) * tb + e) * S, S * W, barF);
     }
 
     for (int t = T - 1; t >= 0; --t) {
@@ -226,7 +244,7 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
           if (have_f) {
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb) {
-              const double2 f2 = *reinterpret_cast<const double2*>(fs + kb * 8 + 2 * tg);
+              const double2 f2 = ld2<IO>(fs + kb * 8 + 2 * tg);
               a = __fma_rn(Vr[r][kb][0], f2.x, a);
               a = __fma_rn(Vr[r][kb][1], f2.y, a);
             }
@@ -264,14 +282,14 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
       //      the first pass) is interleaved with the DMMAs of the next two passes: 8 pivot steps, one per two k-steps.
       double Qxx[4][4][2], Qxu[4][2];
       double cinv[M];
-      double* fg = save_fac ? p.fac + idx * (M * M + N * M) : nullptr;
+      IO* fg = save_fac ? p.fac + idx * (M * M + N * M) : nullptr;
 #pragma unroll
       for (int pi = 0; pi < 5; ++pi) {
         const int i = (pi == 0) ? 4 : pi - 1;
         double acc[5][2];
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
-          const double2 c2 = *reinterpret_cast<const double2*>(Cs + (i * 8 + gr) * S + j * 8 + 2 * tg);
+          const double2 c2 = ld2<IO>(Cs + (i * 8 + gr) * S + j * 8 + 2 * tg);
           acc[j][0] = c2.x; acc[j][1] = c2.y;
         }
         __syncwarp();
@@ -280,7 +298,7 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
         // release; a fence.proxy.async here costs ~6 % of the kernel (it drains every outstanding memory operation)
         // and is only required in the other direction (generic writes later read by the async proxy).
         if (t > 0 && lane == 0) {                      // refill this row block for the next step
-          if (pi == 0) mbar_arrive_expect_tx(barC, S * S * 8);
+          if (pi == 0) mbar_arrive_expect_tx(barC, S * S * W);
           stage_C_rows(t - 1, i);
         }
         if (pi == 1) {
@@ -322,7 +340,7 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
         }
         if (pi == 2 && lane >= M && lane < 2 * M) {    // lanes 8..15 hold the columns of Quu^-1
 #pragma unroll
-          for (int ii = 0; ii < M; ++ii) { Qi_s[ii * LDU + lane - M] = cinv[ii]; if (fg) fg[ii * M + lane - M] = cinv[ii]; }
+          for (int ii = 0; ii < M; ++ii) { Qi_s[ii * LDU + lane - M] = cinv[ii]; if (fg) fg[ii * M + lane - M] = (IO)cinv[ii]; }
         }
       }
       __syncwarp();                                    // F_t, f_t, c_t, mv are dead; Qux, Quu^-1, qu are complete
@@ -342,20 +360,20 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
         const double2 qi2 = *reinterpret_cast<const double2*>(Qi_s + gr * LDU + 2 * tg);
         const double2 qu2 = *reinterpret_cast<const double2*>(qu_s + 2 * tg);
         const double kk = -quad_sum(__fma_rn(qi2.x, qu2.x, qi2.y * qu2.y));
-        if (tg == 0) { kk_s[gr] = kk; p.ks[idx * M + gr] = kk; }
+        if (tg == 0) { kk_s[gr] = kk; p.ks[idx * M + gr] = (IO)kk; }
         __syncwarp();                                  // every lane has read the Qux panel: K may overwrite it
-        double* Kg = p.Ks + idx * (M * N) + gr * N + 2 * tg;
+        IO* Kg = p.Ks + idx * (M * N) + gr * N + 2 * tg;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const double2 k2 = make_double2(-Kt[c][0], -Kt[c][1]);
           *reinterpret_cast<double2*>(K_s + gr * LDK + c * 8 + 2 * tg) = k2;
-          *reinterpret_cast<double2*>(Kg + c * 8) = k2;
+          st2(Kg + c * 8, k2.x, k2.y);
         }
       }
       if (fg) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-          *reinterpret_cast<double2*>(fg + M * M + (r * 8 + gr) * M + 2 * tg) = make_double2(Qxu[r][0], Qxu[r][1]);
+          st2(fg + M * M + (r * 8 + gr) * M + 2 * tg, Qxu[r][0], Qxu[r][1]);
       }
       __syncwarp();
       // ---- V = Qxx + Qxu K, v = qx + Qxu k.  The reference's extra terms K^T (Qux + Quu K) and K^T (qu + Quu k)
@@ -395,28 +413,30 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
       double* base = sm + st * Cfg::RSTG;
       const size_t idx = (size_t)t * tb + e;
       const bool hasF = t < T - 1;
-      if (hasF) stage_F_rows(base + Cfg::RF, p.F + idx * (N * S), lane);
-      const double* Kg = p.Ks + idx * (M * N);
+      if (hasF) stage_F_rows<IO>(reinterpret_cast<IO*>(base + Cfg::RF), p.F + idx * (N * S), lane);
+      const IO* Kg = p.Ks + idx * (M * N);
+      constexpr int CPR = N / EP;                  // 16-byte chunks per row of K (fp64: 128 chunks in all, 16 per row)
 #pragma unroll
-      for (int it = 0; it < M * N / 64; ++it) {    // 128 chunks, 16 per row of K
-        const int q = it * 32 + lane, row = q >> 4, cc = q & 15;
-        cp_async16(base + Cfg::RK + row * LDKR + cc * 2, Kg + q * 2);
+      for (int it = 0; it < M * CPR / 32; ++it) {
+        const int q = it * 32 + lane, row = q / CPR, cc = q % CPR;
+        cp_async16(reinterpret_cast<IO*>(base + Cfg::RK) + row * LDKR + cc * EP, Kg + q * EP);
       }
-      if (lane < M / 2) cp_async16(base + Cfg::Rk + lane * 2, p.ks + idx * M + lane * 2);
-      if (hasF && have_f && lane >= 16) cp_async16(base + Cfg::Rf + (lane - 16) * 2, p.f + idx * N + (lane - 16) * 2);
+      if (lane < M / EP) cp_async16(reinterpret_cast<IO*>(base + Cfg::Rk) + lane * EP, p.ks + idx * M + lane * EP);
+      if (hasF && have_f && lane >= 16 && lane - 16 < N / EP)
+        cp_async16(reinterpret_cast<IO*>(base + Cfg::Rf) + (lane - 16) * EP, p.f + idx * N + (lane - 16) * EP);
       cp_async_commit();
     };
     load_roll(0, 0);
-    xs[lane] = p.x0[(size_t)e * N + lane];
+    xs[lane] = (double)p.x0[(size_t)e * N + lane];
     int st = 0;
     for (int t = 0; t < T; ++t) {
       cp_async_wait<0>();
       __syncwarp();
       if (t + 1 < T) load_roll(t + 1, st ^ 1);
-      const double* Fs = sm + st * Cfg::RSTG + Cfg::RF;
-      const double* fs = sm + st * Cfg::RSTG + Cfg::Rf;
-      const double* Kt = sm + st * Cfg::RSTG + Cfg::RK;
-      const double* kt = sm + st * Cfg::RSTG + Cfg::Rk;
+      const IO* Fs = reinterpret_cast<const IO*>(sm + st * Cfg::RSTG + Cfg::RF);
+      const IO* fs = reinterpret_cast<const IO*>(sm + st * Cfg::RSTG + Cfg::Rf);
+      const IO* Kt = reinterpret_cast<const IO*>(sm + st * Cfg::RSTG + Cfg::RK);
+      const IO* kt = reinterpret_cast<const IO*>(sm + st * Cfg::RSTG + Cfg::Rk);
       {   // u = K x + k : control g, interleaved quarter of the states per lane (bank-conflict free with LDKR = 36)
         double a = 0.0;
 #pragma unroll
@@ -426,9 +446,9 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
       }
       __syncwarp();
       const size_t idx = (size_t)t * tb + e;
-      if (p.x) p.x[idx * N + lane] = xs[lane];
-      if (p.u && lane < M) p.u[idx * M + lane] = xs[N + lane];
-      if (p.tau_out) { p.tau_out[idx * S + lane] = xs[lane]; if (lane < M) p.tau_out[idx * S + N + lane] = xs[N + lane]; }
+      if (p.x) p.x[idx * N + lane] = (IO)xs[lane];
+      if (p.u && lane < M) p.u[idx * M + lane] = (IO)xs[N + lane];
+      if (p.tau_out) { p.tau_out[idx * S + lane] = (IO)xs[lane]; if (lane < M) p.tau_out[idx * S + N + lane] = (IO)xs[N + lane]; }
       if (t < T - 1) {   // x' = F [x; u] + f : one state per lane, four accumulation chains
         double a0 = have_f ? fs[lane] : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll

@@ -53,19 +53,22 @@ static bool dmma_cta_kernel() {        // DMPC_DMMA_CTA=1: first-generation CTA-
   return v == 1;
 }
 
-// n=32, m=8, fp64: Riccati sweep on DMMA.  Default = warp-per-element register-resident kernel
+// n=32, m=8: Riccati sweep on DMMA.  Default = warp-per-element register-resident kernel
 // (lqr_dmma_warp.cuh, rollout fused in); rollout-only calls use a compact launch of the generic kernel.
-static int launch_lqr_solve_dmma(const LqrParams<double>& p, cudaStream_t st, long long* nl) {
-  if ((p.flags & LQR_DO_FACTOR) && !dmma_cta_kernel()) {
+// R = float: the same kernel with float tensors in HBM and in the staging buffers, fp64 arithmetic.
+template <typename R>
+static int launch_lqr_solve_dmma(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
+  constexpr bool F64 = std::is_same<R, double>::value;
+  if ((p.flags & LQR_DO_FACTOR) && !(F64 && dmma_cta_kernel())) {
     constexpr int WPC = 4;
     const size_t smem = (size_t)WPC * WarpCfg::TOTAL * sizeof(double);
-    auto kern = lqr_factor_dmma_warp_kernel<WPC>;
+    auto kern = lqr_factor_dmma_warp_kernel<WPC, R>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DMPC_ERR_CUDA;
     kern<<<(p.B + WPC - 1) / WPC, WPC * 32, smem, st>>>(p);
     if (nl) ++*nl;
     return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
   }
-  if (p.flags & LQR_DO_FACTOR) {
+  if constexpr (F64) if (p.flags & LQR_DO_FACTOR) {
     using Cfg = DmmaCfg<32, 8>;
     const size_t smem = (size_t)Cfg::TOTAL * sizeof(double);
     auto kern = lqr_factor_dmma_kernel<32, 8>;
@@ -85,10 +88,10 @@ static int launch_lqr_solve_dmma(const LqrParams<double>& p, cudaStream_t st, lo
     return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
   }
   if (p.flags & LQR_DO_ROLLOUT) {
-    LqrParams<double> q = p;
+    LqrParams<R> q = p;
     q.flags = LQR_DO_ROLLOUT;
-    const LqrLayout L = lqr_layout<double>(q.n, q.m, false, true);
-    return do_launch(lqr_solve_kernel<double, 32, 8, 32>, q, 32, (size_t)L.stride * sizeof(double), q.B, st, nl);
+    const LqrLayout L = lqr_layout<R>(q.n, q.m, false, true);
+    return do_launch(lqr_solve_kernel<R, 32, 8, 32>, q, 32, (size_t)L.stride * sizeof(R), q.B, st, nl);
   }
   return DMPC_OK;
 }
@@ -96,10 +99,8 @@ static int launch_lqr_solve_dmma(const LqrParams<double>& p, cudaStream_t st, lo
 template <typename R>
 int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
   const ShapeInfo si = pick_shape_impl(p.n, p.m);
-  if constexpr (std::is_same<R, double>::value) {
-    if (p.n == 32 && p.m == 8 && !(p.flags & LQR_MASKED) && p.c && p.c_scale == 1.0 && dmma_enabled())
-      return launch_lqr_solve_dmma(p, st, nl);
-  }
+  if (p.n == 32 && p.m == 8 && !(p.flags & LQR_MASKED) && p.c && p.c_scale == R(1) && dmma_enabled())
+    return launch_lqr_solve_dmma<R>(p, st, nl);
   const bool compact = !(p.flags & LQR_DO_FACTOR);
   const LqrLayout L = lqr_layout<R>(p.n, p.m, (p.flags & LQR_SAVE_FAC) != 0, compact);
   const size_t sb = (size_t)L.stride * sizeof(R);

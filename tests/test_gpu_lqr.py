@@ -141,13 +141,35 @@ def test_linearity_property_full_size(ctx):
 
 @pytest.mark.parametrize("T,B,with_f,sym", [(1, 3, True, True), (2, 6, True, True), (3, 1, False, True), (7, 9, False, False),
                                            (16, 130, True, False)])
-def test_dmma_warp_kernel_edge_cases(ctx, T, B, with_f, sym):
-    """n=32, m=8 fp64 runs lqr_factor_dmma_warp_kernel (one warp per element, 4 per CTA): horizon edge cases, batch sizes
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_dmma_warp_kernel_edge_cases(ctx, T, B, with_f, sym, dtype):
+    """n=32, m=8 runs lqr_factor_dmma_warp_kernel (one warp per element, 4 per CTA): horizon edge cases, batch sizes
     that leave warps of the last CTA idle, f=None, and a NON-symmetric C (the reference never symmetrises C, and the
-    kernel's operand re-use must not assume it)."""
+    kernel's operand re-use must not assume it).  float32 = the same kernel with float tensors in HBM and in the
+    staging buffers (different row pitches, copy sizes and chunk counts), fp64 arithmetic."""
     n, m = 32, 8
     pr = lqr_problem(T * 31 + B, T, B, n, m, with_f=with_f, sym=sym)
     ox, ou, oK, ok = olqr.lqr_solve(pr["x0"], pr["C"], pr["c"], pr["F"], pr["f"], n, m)
-    r = run_solve(ctx, pr, np.float64)
-    assert rel_err(r["Ks"].download(), oK) < 1e-10 and rel_err(r["ks"].download(), ok) < 1e-10
-    assert rel_err(r["x"].download(), ox) < 1e-10 and rel_err(r["u"].download(), ou) < 1e-10
+    r = run_solve(ctx, pr, dtype)
+    tol = TOL[dtype]
+    assert rel_err(r["Ks"].download(), oK) < tol and rel_err(r["ks"].download(), ok) < tol
+    assert rel_err(r["x"].download(), ox) < tol and rel_err(r["u"].download(), ou) < tol
+
+
+def test_dmma_warp_kernel_fp32_is_rounded_fp64(ctx):
+    """The fp32 n=32/m=8 path computes in fp64 on float inputs: on inputs that are exactly representable in float its
+    gains equal the fp64 path's gains rounded to float, and the trajectory differs only by the float rounding of the stored
+    K_t, k_t that the rollout re-reads."""
+    T, B, n, m = 20, 37, 32, 8
+    pr = lqr_problem(991, T, B, n, m, with_f=True, sym=False)
+    for k in ("x0", "C", "c", "F", "f"):
+        pr[k] = pr[k].astype(np.float32).astype(np.float64)
+    r64 = run_solve(ctx, pr, np.float64)
+    r32 = run_solve(ctx, pr, np.float32)
+    K64, K32 = r64["Ks"].download(), r32["Ks"].download()
+    assert K32.dtype == np.float32
+    # gains: the fp64 values rounded to float (one float ulp of slack)
+    assert np.allclose(K32, K64.astype(np.float32), rtol=2.4e-7, atol=1e-12)
+    assert np.allclose(r32["ks"].download(), r64["ks"].download().astype(np.float32), rtol=2.4e-7, atol=1e-12)
+    assert rel_err(r32["x"].download(), r64["x"].download()) < 1e-5
+    assert rel_err(r32["u"].download(), r64["u"].download()) < 1e-5
