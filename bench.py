@@ -231,6 +231,47 @@ def make_problem_torch(torch, dev, n, m, T, B, seed):
     return dict(x0=x0, C=C, c=c, F=F, f=f, gx=gx, gu=gu)
 
 
+def dmma_shape(n, m):
+    return (n, m) == (32, 8)
+
+
+def fp32_step(torch, ctx, chunk, n, m, T, B, stream):
+    """fwd+bwd of one chunk through the fp32 API (dtype DMPC_F32): inputs cast to float on the device, outputs checked
+    against the fp64 outputs of the same chunk (north_star tolerance 1e-4 relative)."""
+    import _native
+    pr64, o64 = chunk
+    f32 = torch.float32
+    pr = {k: v.to(f32) for k, v in pr64.items()}
+    o = {k: torch.empty(v.shape, dtype=f32, device=v.device) for k, v in o64.items()}
+    P = lambda t: t.data_ptr()
+    FULL = _native.LQR_FACTOR | _native.LQR_ROLLOUT | _native.LQR_SAVE_FAC
+
+    def step():
+        ctx.lqr_solve(np.float32, T, B, n, m, P(pr["x0"]), P(pr["C"]), P(pr["c"]), P(pr["F"]), T - 1, P(pr["f"]),
+                      P(o["x"]), P(o["u"]), P(o["Ks"]), P(o["ks"]), P(o["fac"]), FULL, stream.cuda_stream)
+        ctx.lqr_adjoint(np.float32, T, B, n, m, P(pr["C"]), P(pr["c"]), P(pr["F"]), P(o["x"]), P(o["u"]), P(pr["gx"]),
+                        P(pr["gu"]), P(o["Ks"]), P(o["fac"]), P(o["dx0"]), P(o["dC"]), P(o["dc"]), P(o["dF"]), P(o["df"]),
+                        _native.ADJ_STRICT_REFERENCE, stream.cuda_stream)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    reps = 6
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    rel = {k: float((o[k].double() - o64[k]).norm() / o64[k].norm()) for k in ("x", "u", "dF")}
+    _, tot_b = algorithmic_bytes(n, m, T, w=4)
+    return {"dtype": "f32 tensors in HBM, f64 arithmetic in the Riccati sweep (lqr_factor_dmma_warp_kernel<4,float>)",
+            "batch": B, "ms_per_step": ms, "solves_per_sec": B / (ms * 1e-3),
+            "whole_step_hbm_frac": B * tot_b / (ms * 1e-3) / 1e9 / measured_peaks()[0],
+            "rel_err_vs_f64_step": rel, "within_1e-4": all(v < 1e-4 for v in rel.values())}
+
+
 def run_b200(args):
     import torch
     import _native
@@ -389,7 +430,7 @@ def run_b200(args):
         fwd_b, tot_b = algorithmic_bytes(n, m, T)
         peak, peak_src = measured_peaks()
         traffic = ncu_traffic()
-        dmma = (n, m) == (32, 8)
+        dmma = dmma_shape(n, m)
         fwd_name = "lqr_factor_dmma_warp_kernel" if dmma else "lqr_solve_kernel"
         s_ = n + m
         dtau_b = 8 * (2 * (T - 1) * n * s_ + T * (m * m + n * m) + T * m * n + 2 * T * s_)        # F twice, factors, K, grads, d-tau
@@ -469,6 +510,16 @@ def run_b200(args):
         exch = {"what": "adjoint with fused (T,B)-sum -> %d doubles (dC|dc|dF|df), then NCCL all_reduce(sum)" % rsz,
                 "adjoint_reduced_ms": float(np.median(red_ms)), "allreduce_ms": float(np.median(ar_ms)), "world": world}
 
+    # ---- the same step through the fp32 API (SURVEY 8d lists config 5 as "fp64 and fp32"): float tensors, reported
+    #      beside the fp64 metric, never instead of it
+    fp32 = None
+    if dmma_shape(n, m) and world == 1 and not args.no_latency:
+        try:
+            fp32 = fp32_step(torch, ctx, chunks[0], n, m, T, Bc, sA)
+        except Exception as ex:
+            fp32 = {"error": repr(ex)[:200]}
+        torch.cuda.empty_cache()
+
     # ---- e2e through the public API with host buffers (rank-local chunk) -----------------
     e2e = None
     try:
@@ -479,6 +530,8 @@ def run_b200(args):
         line["e2e"] = e2e
         if exch is not None:
             line["param_grad_exchange"] = exch
+        if fp32 is not None:
+            line["fp32_step"] = fp32
         if world == 1 and not args.no_cpu:
             Bcpu = cpu_sample_batch(n, m, T)
             cpu_lqr_fwd_bwd(n, m, T, min(Bcpu, 32))
