@@ -10,7 +10,9 @@
  *   - All tensors use the reference's layout: time-major, batch-second, C-contiguous
  *     (lqr_recursion.py:51-66):  x_init[B,n] C[T,B,s,s] c[T,B,s] F[F_T,B,n,s] f[T-1,B,n]
  *     x[T,B,n] u[T,B,m]   with s = n + m and F_T in {T-1, T} (mpc_step.py:83-89).
- *   - dtype: DMPC_F64 (the reference is float64 end to end) or DMPC_F32.
+ *   - dtype: DMPC_F64 (the reference is float64 end to end) or DMPC_F32.  dtype is the element type of
+ *     every tensor argument; kernels compute in that type, except dmpc_lqr_solve at n=32, m=8 with
+ *     DMPC_F32, which widens the float tiles and runs the fp64 tensor-core (DMMA) recursion.
  *   - Pointers named d_* are DEVICE pointers; the call is asynchronous on `stream`
  *     (a cudaStream_t passed as void*; NULL = the handle's stream).
  *   - Pointers named h_* are HOST pointers; those entry points copy in/out and
