@@ -24,9 +24,9 @@ def outputs(dt):
                 dF=torch.empty(T - 1, B, n, s, dtype=dt, device=dev), df=torch.empty(T - 1, B, n, dtype=dt, device=dev))
 
 
-def fwd(npdt, pr, o):
+def fwd(npdt, pr, o, flags=7):
     ctx.lqr_solve(npdt, T, B, n, m, P(pr["x0"]), P(pr["C"]), P(pr["c"]), P(pr["F"]), T - 1, P(pr["f"]), P(o["x"]), P(o["u"]),
-                  P(o["Ks"]), P(o["ks"]), P(o["fac"]), 7, st.cuda_stream)
+                  P(o["Ks"]), P(o["ks"]), P(o["fac"]), flags, st.cuda_stream)
 
 
 def bwd(npdt, pr, o):
@@ -44,18 +44,21 @@ pr32 = {k: v.float() for k, v in pr64.items()}
 del pr64
 torch.cuda.empty_cache()
 o32 = outputs(torch.float32)
-res = {"fwd": [], "bwd": []}
+res = {"fwd": [], "bwd": [], "factor_only": [], "rollout_only": []}
 for it in range(6):
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     e[0].record(st); fwd(np.float32, pr32, o32); e[1].record(st); bwd(np.float32, pr32, o32); e[2].record(st)
+    fwd(np.float32, pr32, o32, 5); e[3].record(st); fwd(np.float32, pr32, o32, 2); e[4].record(st)   # Riccati sweep alone, rollout alone
     torch.cuda.synchronize()
     if it >= 2:
         res["fwd"].append(e[0].elapsed_time(e[1])); res["bwd"].append(e[1].elapsed_time(e[2]))
+        res["factor_only"].append(e[2].elapsed_time(e[3])); res["rollout_only"].append(e[3].elapsed_time(e[4]))
 ms = {k: float(np.median(v)) for k, v in res.items()}
 rel = {k: float((o32[k] - ref[k]).norm() / ref[k].norm()) for k in ref}
 tot = ms["fwd"] + ms["bwd"]
 fb, tb = bench.algorithmic_bytes(n, m, T, w=4)
 print(json.dumps({"workload": "c5 fp32 (lqr_factor_dmma_warp_kernel<4,float> + adjoint kernels)", "batch": B,
-                  "fwd_ms": round(ms["fwd"], 3), "bwd_ms": round(ms["bwd"], 3), "solves_per_sec": B / (tot * 1e-3),
+                  "fwd_ms": round(ms["fwd"], 3), "bwd_ms": round(ms["bwd"], 3),
+                  "factor_only_ms": round(ms["factor_only"], 3), "rollout_only_ms": round(ms["rollout_only"], 3), "solves_per_sec": B / (tot * 1e-3),
                   "algorithmic_bytes_per_solve": tb, "whole_step_gbs": B * tb / (tot * 1e-3) / 1e9,
                   "rel_err_vs_fp64_device": rel}))
