@@ -1,6 +1,8 @@
 """GPU: reference-facing PNQP / MPCstep / LQR_active / BoxDDP classes (names and signatures of
 mpc/pnqp.py, mpc/mpc_step.py, mpc/active_constrained_lqr.py, mpc/box_ddp.py) vs fixtures generated
 from the unmodified reference."""
+import contextlib
+import io
 import warnings
 
 import numpy as np
@@ -187,3 +189,39 @@ def test_boxddp_device_loop_scrambled_norm_long_rows():
     assert out[True][3] == out[False][3]
     assert np.array_equal(out[True][0], out[False][0])
     assert np.array_equal(out[True][1], out[False][1]) and np.array_equal(out[True][2], out[False][2])
+
+
+def test_boxddp_and_backward_against_exact_qp():
+    """The CUDA path against ground truth that shares no code with it (tests/test_oracle_fd_il.py): BoxDDP on a
+    box-constrained linear-quadratic instance lands on the exactly solved QP (to the solver's own stopping tolerance), and
+    the fused-reduction backward of the final MPCstep gives the finite-difference gradient of the imitation loss w.r.t. the
+    shared cost parameters q, p (evaluated at BoxDDP's point, hence the looser tolerance than the oracle-level test)."""
+    import test_oracle_fd_il as ex
+    from box_ddp import BoxDDP
+    from util import QuadCost, LinDx
+    T, B, n, m, s = ex.T, ex.B, ex.n, ex.m, ex.s
+    pr = ex._problem()
+    q = np.array([1.0, 0.8, 1.2, 0.5, 0.7])
+    p = np.array([0.2, -0.1, 0.3, 0.1, -0.2])
+    C, c = ex._cost(q, p, pr)
+    solver = BoxDDP(T=T, u_lower=ex.LO, u_upper=ex.HI, n_batch=B, n_state=n, n_ctrl=m, u_init=None, eps=1e-11, max_iter=60,
+                    not_improved_lim=60, line_search_decay=0.2, max_line_search_iter=10, exit_unconverged=False,
+                    coupling="element")
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        x, u, _ = solver((pr[3], QuadCost(C, c), LinDx(pr[1], pr[2])))
+    x, u = arr(x), arr(u)
+    sets = (np.abs(u - ex.LO) <= 1e-8, np.abs(u - ex.HI) <= 1e-8)
+    X, U = ex._exact_qp(C, c, pr, *sets)                    # asserts the KKT signs of the active set the GPU found
+    assert 0.15 < (sets[0] | sets[1]).mean() < 0.7
+    assert np.max(np.abs(u - U)) < 1e-4 and np.max(np.abs(x - X)) < 5e-4
+    gu = 2.0 * (u - pr[5]) / u.size
+    g = solver.last_step.backward_reduced_numpy(None, gu)    # (dx0, sum dC, sum dc, sum dF, sum df)
+    gq, gp = np.diag(g[1]), g[2]
+    h = 1e-5
+    for i in range(s):
+        e = np.zeros(s); e[i] = h
+        fq = (ex._loss(ex._solve_exact(q + e, p, pr, sets)[3], pr) - ex._loss(ex._solve_exact(q - e, p, pr, sets)[3], pr)) / (2 * h)
+        fp = (ex._loss(ex._solve_exact(q, p + e, pr, sets)[3], pr) - ex._loss(ex._solve_exact(q, p - e, pr, sets)[3], pr)) / (2 * h)
+        assert abs(gq[i] - fq) <= 2e-3 * abs(fq) + 2e-6, ("q", i, gq[i], fq)
+        assert abs(gp[i] - fp) <= 2e-3 * abs(fp) + 2e-6, ("p", i, gp[i], fp)
