@@ -96,6 +96,32 @@ template <> __device__ __forceinline__ double2 ld2<float>(const float* p) {
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 __device__ __forceinline__ void st2(float* p, double a, double b) { *reinterpret_cast<float2*>(p) = make_float2((float)a, (float)b); }
 
+#ifdef DMPC_GJ_FASTPATH
+// EXPERIMENT (off by default; build with `make EXTRA=-DDMPC_GJ_FASTPATH`): pivot-free Gauss-Jordan step with an acceptance
+// test, for the next round's A/B.  The static mix (profiles/r1/sass_mix_factor_warp.txt) shows the pivoted inverse is a
+// third of the sweep's instruction stream.  Quu has a positive-definite symmetric part in every BASELINE workload, where
+// elimination without row exchanges is stable; `bad` is raised when a pivot is smaller than 2^-6 of the largest entry
+// below it (compared on the high word), and the caller then redoes the inverse with the pivoted steps.  Every lane sees
+// the same broadcast column, so `bad` is warp uniform.
+template <int M>
+__device__ __forceinline__ void gj_step_nopivot(double (&c)[M], const int k, unsigned& bad) {
+  constexpr unsigned FULL = 0xffffffffu;
+  double pc[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) pc[i] = __shfl_sync(FULL, c[i], k);
+  unsigned mx = 0u;
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+    if (i > k) mx = max(mx, abs_hi(pc[i]));
+  bad |= (abs_hi(pc[k]) + (6u << 20) < mx) ? 1u : 0u;
+  const double ck = c[k] * fast_rcp2(pc[k]);
+  c[k] = ck;
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+    if (i != k) c[i] = __fma_rn(-pc[i], ck, c[i]);
+}
+#endif
+
 struct WarpCfg {
   static constexpr int N = 32, M = 8, S = 40;
   // F buffer: row pitch 42 doubles -> the four fragment rows 2t+e of a half-warp fall in distinct 32-byte
@@ -109,7 +135,12 @@ struct WarpCfg {
   static constexpr int LDU = 12;     // Quu / Quu^-1 [8][12]: A fragments by rows g
   static constexpr int LDK = 34;     // K panel [8][34]: B fragments by rows 2t+e (aliases the Qux panel)
   static constexpr int OQux = OSCR, OK = OQux, OQuu = OQux + M * LDQ, OQi = OQuu + M * LDU, Oqu = OQi + M * LDU,
-                       Okk = Oqu + M, Omv = Okk + M, Obar = Omv + N, TOTAL = Obar + 2;   // two mbarriers per warp
+                       Okk = Oqu + M, Omv = Okk + M, Obar = Omv + N;                     // two mbarriers per warp
+#ifdef DMPC_GJ_FASTPATH
+  static constexpr int Oqx = Obar + 2, TOTAL = Oqx + N;   // q_x gets its own slot: the Quu panel must survive for the fallback
+#else
+  static constexpr int TOTAL = Obar + 2;
+#endif
   // rollout: two stages {F, f, K_t [8][36], k_t} carved from the same region, then x|u and x_next
   static constexpr int LDKR = 36;
   static constexpr int RF = 0, Rf = RF + N * LDF, RK = Rf + N, Rk = RK + M * LDKR, RSTG = Rk + M;
@@ -212,7 +243,12 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
     // V_t as accumulator-layout registers: Vr[r][kb][e] = V[8r+g][8kb+2t+e];  vr[r] = v[8r+g]
     // v_t and q_x live in shared memory between their producer and consumer (v aliases mv, q_x aliases Quu)
     double Vr[4][4][2];
+#ifdef DMPC_GJ_FASTPATH
+    double* v_s = mv_s; double* qx_s = sm + Cfg::Oqx;
+    unsigned gj_bad = 0u;
+#else
     double* v_s = mv_s; double* qx_s = Quu_s;
+#endif
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
 #pragma unroll
@@ -317,14 +353,38 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
 #pragma unroll
               for (int j = 0; j < 5; ++j) dmma(acc[j], a, WT[j][r][ee]);
               qa = __fma_rn(a, ee ? m2.y : m2.x, qa);
+#ifdef DMPC_GJ_FASTPATH
+              if ((pi == 1 || pi == 2) && ee == 1) gj_step_nopivot<M>(cinv, (pi - 1) * 4 + r, gj_bad);
+#else
               if ((pi == 1 || pi == 2) && ee == 1) gj_step<M>(cinv, (pi - 1) * 4 + r);
+#endif
             }
           }
           qa = quad_sum(qa);
         } else if (pi == 1 || pi == 2) {
 #pragma unroll
+#ifdef DMPC_GJ_FASTPATH
+          for (int r = 0; r < 4; ++r) gj_step_nopivot<M>(cinv, (pi - 1) * 4 + r, gj_bad);
+#else
           for (int r = 0; r < 4; ++r) gj_step<M>(cinv, (pi - 1) * 4 + r);
+#endif
         }
+#ifdef DMPC_GJ_FASTPATH
+        if (pi == 2 && gj_bad) {                       // rare, warp uniform: redo the inverse with row exchanges
+#pragma unroll
+          for (int ii = 0; ii < M; ++ii) cinv[ii] = (lane < M) ? Quu_s[ii * LDU + lane] : ((lane - M == ii) ? 1.0 : 0.0);
+#pragma unroll 1
+          for (int k = 0; k < M; ++k) {
+            switch (k) {                               // gj_step needs a compile-time row index
+              case 0: gj_step<M>(cinv, 0); break; case 1: gj_step<M>(cinv, 1); break;
+              case 2: gj_step<M>(cinv, 2); break; case 3: gj_step<M>(cinv, 3); break;
+              case 4: gj_step<M>(cinv, 4); break; case 5: gj_step<M>(cinv, 5); break;
+              case 6: gj_step<M>(cinv, 6); break; default: gj_step<M>(cinv, 7); break;
+            }
+          }
+          gj_bad = 0u;
+        }
+#endif
         qa += cs[i * 8 + gr];
         if (i == 4) {
 #pragma unroll

@@ -2,7 +2,7 @@
 (cuobjdump -sass): the loop is the largest backward branch whose body contains the DMMAs.  No GPU needed."""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-obj = os.path.join(ROOT, "chainer-differentiable-mpc_b200", "csrc", "build", "lqr_launch_f64.o")
+obj = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "chainer-differentiable-mpc_b200", "csrc", "build", "lqr_launch_f64.o")
 fun = "_ZN4dmpc27lqr_factor_dmma_warp_kernelILi4EdEEvNS_9LqrParamsIT0_EE"
 sass = subprocess.run(["cuobjdump", "-sass", "-fun", fun, obj], capture_output=True, text=True, check=True).stdout
 ins = []
