@@ -47,10 +47,13 @@ def algorithmic_bytes(n, m, T, w=8):
 
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
+    try:
         with open(path) as fh:
-            d = json.load(fh)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            v = float(json.load(fh)["hbm_gbs"])
+        if v > 0:
+            return v, "measured (MEASURED_PEAKS.json)"
+    except (OSError, ValueError, KeyError, TypeError):
+        pass
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
