@@ -106,6 +106,47 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def elem_rel_err(a, b, floor_frac=1e-3):
+    """Element-relative error with an absolute floor (same definition as tests/_helpers.rel_err): max over entries of
+    |a-b| / (|b| + floor), floor = floor_frac x the largest magnitude of the entry's own (timestep, element) block."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    if b.size == 0:
+        return 0.0
+    ab = np.abs(b)
+    gmax = float(np.max(ab))
+    if b.ndim >= 3:
+        sl = np.max(ab, axis=tuple(range(2, b.ndim)), keepdims=True)
+    elif b.ndim == 2:
+        sl = np.max(ab, axis=1, keepdims=True)
+    else:
+        sl = gmax
+    floor = np.maximum(np.maximum(floor_frac * sl, 1e-6 * gmax), 1e-300)
+    d = np.abs(a - b)
+    if not np.all(np.isfinite(d)):
+        return float("inf")
+    return float(np.max(d / (ab + floor)))
+
+
+def parity_vs_oracle(chunk, n, m, T, k=16):
+    """Checker leg (oracle = test infrastructure): the first k batch elements of the TIMED chunk - inputs and the outputs
+    the last timed step left in HBM - against the oracle restatement of DiffLqr.apply + .backward."""
+    from oracle import lqr as olqr
+    pr, out = chunk
+    k = min(k, pr["x0"].shape[0])
+    h = lambda t: np.ascontiguousarray(t[:, :k].cpu().numpy())
+    x0 = pr["x0"][:k].cpu().numpy()
+    C, c, F, f, gx, gu = h(pr["C"]), h(pr["c"]), h(pr["F"]), h(pr["f"]), h(pr["gx"]), h(pr["gu"])
+    ox, ou, oK, ok = olqr.lqr_solve(x0, C, c, F, f, n, m)
+    og = olqr.difflqr_backward(x0, C, c, F, ox, ou, gx, gu, n, m)
+    errs = {"x": elem_rel_err(h(out["x"]), ox), "u": elem_rel_err(h(out["u"]), ou), "Ks": elem_rel_err(h(out["Ks"]), oK),
+            "ks": elem_rel_err(h(out["ks"]), ok), "dx0": elem_rel_err(out["dx0"][:k].cpu().numpy(), og[0])}
+    for name, w in zip(("dC", "dc", "dF", "df"), og[1:]):
+        errs[name] = elem_rel_err(h(out[name]), w)
+    return {"max_rel": max(errs.values()), "per_output": errs, "elements": k,
+            "metric": "element-relative, floor 1e-3 x block max (tests/_helpers.rel_err)",
+            "oracle": "oracle/lqr.py (numpy restatement pinned to the live reference by tests/golden/make_golden.py)"}
+
+
 # ------------------------------------------------------------------------------------- CPU port timing
 def cpu_lqr_fwd_bwd(n, m, T, Bc, seed=0):
     """One DiffLqr.apply + .backward with the oracle port (numpy, all BLAS threads)."""
@@ -427,6 +468,12 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
     ok = all(bool(torch.isfinite(o["x"]).all().item() and torch.isfinite(o["dF"]).all().item()) for _, o in chunks)
+    parity = None
+    if rank == 0:
+        try:
+            parity = parity_vs_oracle(chunks[0], n, m, T)
+        except Exception as ex:   # report, do not hide
+            parity = {"max_rel": None, "error": repr(ex)[:200]}
 
     line = None
     if rank == 0:
@@ -492,7 +539,8 @@ def run_b200(args):
                                  "512 MB flush buffer rewritten between timed steps (working set %.2f GB/GPU), each step "
                                  "timed by its own event pair" % (B * tot_b / 1e9),
                            "finite_outputs": ok},
-                "roofline": roof, "clocks": clocks, "gpu_launches": launches}
+                "roofline": roof, "clocks": clocks, "gpu_launches": launches,
+                "parity_max_rel": parity["max_rel"], "parity": parity}
 
     # ---- the one exchange step of a training iteration: (T,B_local)-reduce the learned-dynamics
     #      gradient dF and all-reduce(sum) it over the ranks (NCCL); reported, not part of the solve metric

@@ -66,8 +66,53 @@ class _PlainFunctionNode:
         return tuple(self._out[i] for i in self._ro)
 
 
+class _PlainParameter:
+    """chainer.Parameter stand-in when Chainer is absent: `.array`, `.grad`, numpy conversion."""
+
+    def __init__(self, initializer=None, name=None):
+        self.array = None if initializer is None else np.array(initializer)
+        self.grad = None
+        self.name = name
+
+    data = property(lambda self: self.array)
+    shape = property(lambda self: self.array.shape)
+    dtype = property(lambda self: self.array.dtype)
+
+    def __array__(self, dtype=None, copy=None):
+        return self.array if dtype is None else self.array.astype(dtype)
+
+    def cleargrad(self):
+        self.grad = None
+
+
+class _PlainLink:
+    """chainer.Link stand-in: init_scope, __call__ -> forward, params(), cleargrads()."""
+    xp = np
+
+    def __init__(self):
+        pass
+
+    def init_scope(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def __call__(self, *a, **k):
+        return self.forward(*a, **k)
+
+    def params(self):
+        for v in self.__dict__.values():
+            if isinstance(v, _PlainParameter):
+                yield v
+
+    def cleargrads(self):
+        for p in self.params():
+            p.grad = None
+
+
 FunctionNodeBase = _fn.FunctionNode if HAVE_CHAINER else _PlainFunctionNode
 LinkBase = _chainer.Link if HAVE_CHAINER else object
+NetLinkBase = _chainer.Link if HAVE_CHAINER else _PlainLink      # base of the LqrNet* / MpcNet_* model links
+Parameter = _chainer.Parameter if HAVE_CHAINER else _PlainParameter
 
 
 def as_f(x, dtype=None):

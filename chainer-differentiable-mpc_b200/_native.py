@@ -12,7 +12,9 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdiffmpc_b200.so")
+# DIFFMPC_LIB points at another build of the SAME library (A/B runs of kernel variants under profiles/tools); the
+# product default is the in-tree libdiffmpc_b200.so next to this file.
+LIB_PATH = os.environ.get("DIFFMPC_LIB") or os.path.join(_HERE, "libdiffmpc_b200.so")
 
 F64, F32 = 0, 1
 LQR_FACTOR, LQR_ROLLOUT, LQR_SAVE_FAC = 1, 2, 4

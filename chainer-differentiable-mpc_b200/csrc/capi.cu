@@ -98,7 +98,7 @@ static int mpc_forward_impl(dmpc_handle h, int T, int B, int n, int m, const voi
   p.C = (const R*)C; p.c = (const R*)c; p.F = (const R*)F; p.f = (const R*)f;
   p.x_nom = (const R*)x_nom; p.u_nom = (const R*)u_nom; p.lo = (const R*)lo; p.hi = (const R*)hi;
   p.tC = (const R*)tC; p.tc = (const R*)tc; p.tF = (const R*)tF; p.tf = (const R*)tf;
-  for (int i = 0; i < 5; ++i) p.dyn_params[i] = dynp ? (R)dynp[i < 3 ? i : i] : R(0);
+  for (int i = 0; i < 5; ++i) p.dyn_params[i] = dynp ? (R)dynp[i] : R(0);
   p.x = (R*)x; p.u = (R*)u; p.Ks = (R*)Ks; p.ks = (R*)ks; p.u_first = (R*)u_first; p.objs = (R*)objs;
   p.costs = (R*)costs; p.old_costs = (R*)old_costs; p.alphas = (R*)alphas; p.n_qp = (int*)n_qp;
   p.free_mask = (unsigned char*)free_m; p.n_ls = (int*)n_ls; p.flags = (int*)flags;

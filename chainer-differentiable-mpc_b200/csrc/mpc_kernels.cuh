@@ -203,7 +203,7 @@ struct MpcFwdParams {
   const R* lo; const R* hi;                                 // [T,B,m]
   const R* tC; const R* tc;                                 // true QuadCost
   const R* tF; const R* tf;                                 // true LinDx (dynamics == LINEAR); tf nullable
-  R dyn_params[5];                                          // pendulum (g, m, l[, d, b])
+  R dyn_params[5];                                          // pendulum (g, m, l, dt, max_torque); 0 -> 0.05 / 2.0
   R* x; R* u;                                               // new trajectory
   R* Ks; R* ks;                                             // [T,B,m,n], [T,B,m]
   R* u_first;                                               // alpha = 1 controls (for full_du_norm)
@@ -218,7 +218,7 @@ struct MpcFwdParams {
 template <typename R>
 __device__ __forceinline__ void pendulum_step(const R* par, const R* x, R u, R* xn) {
   const R g = par[0], mass = par[1], l = par[2];
-  const R dt = R(0.05), maxu = R(2.0);
+  const R dt = par[3] > R(0) ? par[3] : R(0.05), maxu = par[4] > R(0) ? par[4] : R(2.0);   // PendulumDx.dt / .max_torque
   const R uc = fmin(fmax(u, -maxu), maxu);
   const R cth = x[0], sth = x[1], dth = x[2];
   const R th = atan2(sth, cth);
@@ -580,7 +580,7 @@ __global__ void traj_kernel(TrajParams<R> p) {
       if (p.Fout) {
         // analytic Jacobian of the `simple` pendulum step; F = [R S], f = x' - R x - S u (approximate.py:111-114)
         const R g = p.dyn_params[0], mass = p.dyn_params[1], l = p.dyn_params[2];
-        const R dt = R(0.05), maxu = R(2.0);
+        const R dt = p.dyn_params[3] > R(0) ? p.dyn_params[3] : R(0.05), maxu = p.dyn_params[4] > R(0) ? p.dyn_params[4] : R(2.0);
         const R c = tau[0], sn = tau[1], uraw = tau[3];
         const R r2 = c * c + sn * sn;
         const R dth_dc = -sn / r2, dth_ds = c / r2;

@@ -6,8 +6,8 @@ backward = the KKT adjoint (reference :78-142) re-using those factors instead of
 Gradient conventions follow the reference bit-for-bit by default (quirks Q1/Q2 of SURVEY.md);
 pass strict_reference=False for the mathematically correct dC / df.
 
-LqrNet / LqrNet_cost_dx (reference :145-248) need chainer.Link/Parameter and are defined only
-when Chainer is importable.
+LqrNet / LqrNet_cost_dx (reference :145-248) are chainer.Links when Chainer is importable and plain objects with the
+same call protocol otherwise; `backward_numpy` is their fused-reduction gradient path.
 """
 import os
 import sys
@@ -150,48 +150,67 @@ class DiffLqr(FunctionNodeBase):
         return tuple(wrap(g) for g in self.backward_numpy(gx, gu))
 
 
-if HAVE_CHAINER:
-    import chainer
-    import chainer.functions as F
-    from util import expand_time_batch
+from _compat import NetLinkBase, Parameter  # noqa: E402
+from util import expand_time_batch  # noqa: E402
 
-    class LqrNet(LinkBase):
-        """Learn A, B through the LQR layer (reference :145-198; same seeding, :167-171)."""
 
-        def __init__(self, T, n_batch, n_state, n_ctrl, seed):
-            super().__init__()
-            self.T, self.n_batch, self.n_state, self.n_ctrl = T, n_batch, n_state, n_ctrl
-            self.n_sc = n_state + n_ctrl
-            with self.init_scope():
-                np.random.seed(seed)
-                A = np.eye(n_state) + 0.2 * np.random.randn(n_state, n_state)
-                self.A = chainer.Parameter(A.astype("f8"))
-                self.B = chainer.Parameter(np.random.randn(n_state, n_ctrl).astype("f8"))
-            self.lqr_layer = DiffLqr(T, n_batch, n_state, n_ctrl)
+def _cat_ab(A, B):
+    if HAVE_CHAINER:
+        from chainer import functions as F
+        return F.concat((A, B), axis=1)
+    return np.concatenate((A.array, B.array), axis=1)
 
-        def forward(self, inputs):
-            x_init, C, c, f = inputs
-            large_f = expand_time_batch(F.concat((self.A, self.B), axis=1), self.T - 1, self.n_batch)
-            return self.lqr_layer.apply((x_init, C, c, large_f, f))
 
-    class LqrNet_cost_dx(LinkBase):
-        """Learn A, B, C, c (reference :201-248; C = I + 0.2 randn is NOT symmetric, Q10)."""
+class LqrNet(NetLinkBase):
+    """Learn A, B through the LQR layer (reference :145-198; same seeding, :167-171).  `backward_numpy` is the fused
+    path: (T,B)-sum of dF inside the adjoint kernel -> A.grad, B.grad without the [T-1,B,n,s] tensor."""
 
-        def __init__(self, T, n_batch, n_state, n_ctrl, seed):
-            super().__init__()
-            self.T, self.n_batch, self.n_state, self.n_ctrl = T, n_batch, n_state, n_ctrl
-            self.n_sc = n_state + n_ctrl
-            with self.init_scope():
-                np.random.seed(seed)
-                self.A = chainer.Parameter((np.eye(n_state) + 0.2 * np.random.randn(n_state, n_state)).astype("f8"))
-                self.B = chainer.Parameter(np.random.randn(n_state, n_ctrl).astype("f8"))
-                self.C = chainer.Parameter((np.eye(self.n_sc) + 0.2 * np.random.randn(self.n_sc, self.n_sc)).astype("f8"))
-                self.c = chainer.Parameter(np.random.randn(self.n_sc).astype("f8"))
-            self.lqr_layer = DiffLqr(T, n_batch, n_state, n_ctrl)
+    def __init__(self, T, n_batch, n_state, n_ctrl, seed):
+        super().__init__()
+        self.T, self.n_batch, self.n_state, self.n_ctrl = T, n_batch, n_state, n_ctrl
+        self.n_sc = n_state + n_ctrl
+        with self.init_scope():
+            np.random.seed(seed)
+            A = np.eye(n_state).astype("float") + 0.2 * np.random.randn(n_state, n_state).astype("float")
+            self.A = Parameter(A)
+            self.B = Parameter(np.random.randn(n_state, n_ctrl).astype("float"))
+        self.lqr_layer = DiffLqr(T, n_batch, n_state, n_ctrl)
 
-        def forward(self, inputs):
-            x_init, f = inputs
-            large_f = expand_time_batch(F.concat((self.A, self.B), axis=1), self.T - 1, self.n_batch)
-            C = expand_time_batch(self.C, self.T, self.n_batch)
-            c = expand_time_batch(self.c, self.T, self.n_batch)
-            return self.lqr_layer.apply((x_init, C, c, large_f, f))
+    def forward(self, inputs):
+        x_init, C, c, f = inputs
+        large_f = expand_time_batch(_cat_ab(self.A, self.B), self.T - 1, self.n_batch)
+        return self.lqr_layer.apply((x_init, C, c, large_f, f))
+
+    def backward_numpy(self, grad_x, grad_u):
+        g = self.lqr_layer.backward_reduced_numpy(grad_x, grad_u)      # (dx0, sum dC, sum dc, sum dF, sum df)
+        self.A.grad, self.B.grad = g[3][:, :self.n_state].copy(), g[3][:, self.n_state:].copy()
+        return self.A.grad, self.B.grad
+
+
+class LqrNet_cost_dx(NetLinkBase):
+    """Learn A, B, C, c (reference :201-248; C = I + 0.2 randn is NOT symmetric, Q10)."""
+
+    def __init__(self, T, n_batch, n_state, n_ctrl, seed):
+        super().__init__()
+        self.T, self.n_batch, self.n_state, self.n_ctrl = T, n_batch, n_state, n_ctrl
+        self.n_sc = n_state + n_ctrl
+        with self.init_scope():
+            np.random.seed(seed)
+            self.A = Parameter(np.eye(n_state).astype("float") + 0.2 * np.random.randn(n_state, n_state).astype("float"))
+            self.B = Parameter(np.random.randn(n_state, n_ctrl).astype("float"))
+            self.C = Parameter(np.eye(self.n_sc).astype("float") + 0.2 * np.random.randn(self.n_sc, self.n_sc).astype("float"))
+            self.c = Parameter(np.random.randn(self.n_sc).astype("float"))
+        self.lqr_layer = DiffLqr(T, n_batch, n_state, n_ctrl)
+
+    def forward(self, inputs):
+        x_init, f = inputs
+        large_f = expand_time_batch(_cat_ab(self.A, self.B), self.T - 1, self.n_batch)
+        C = expand_time_batch(self.C, self.T, self.n_batch)
+        c = expand_time_batch(self.c, self.T, self.n_batch)
+        return self.lqr_layer.apply((x_init, C, c, large_f, f))
+
+    def backward_numpy(self, grad_x, grad_u):
+        g = self.lqr_layer.backward_reduced_numpy(grad_x, grad_u)
+        self.C.grad, self.c.grad = g[1].copy(), g[2].copy()
+        self.A.grad, self.B.grad = g[3][:, :self.n_state].copy(), g[3][:, self.n_state:].copy()
+        return self.A.grad, self.B.grad, self.C.grad, self.c.grad

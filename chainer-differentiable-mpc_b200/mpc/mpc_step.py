@@ -38,14 +38,24 @@ MAX_LS_TRIALS = 64            # safety cap of the per-element line search (refer
 
 
 def is_pendulum(dyn):
-    return type(dyn).__name__ == "PendulumDx" or getattr(dyn, "_dmpc_dynamics", None) == "pendulum"
+    """The package's pendulum_dx.PendulumDx (explicit `_dmpc_dynamics` marker) or the reference's
+    env_dx.pendulum.PendulumDx (a chainer.Link: recognised by its class name AND the attributes the device code is a
+    restatement of - n_state 3, n_ctrl 1, params, dt, max_torque); an unrelated class that merely shares the name is
+    not accepted."""
+    if getattr(dyn, "_dmpc_dynamics", None) == "pendulum":
+        return True
+    return (type(dyn).__name__ == "PendulumDx" and getattr(dyn, "n_state", None) == 3 and getattr(dyn, "n_ctrl", None) == 1
+            and all(hasattr(dyn, a) for a in ("params", "dt", "max_torque")))
 
 
 def pendulum_params(dyn):
+    """(g, m, l, dt, max_torque) handed to the device step (env_dx/pendulum.py:40-41,81-97)."""
     if hasattr(dyn, "simple") and not dyn.simple:
         raise NotImplementedError("only the `simple` pendulum model (g, m, l) has device code")
     p = np.asarray(to_xp(dyn.params), dtype=np.float64).ravel()
-    return (float(p[0]), float(p[1]), float(p[2]))
+    dt, maxu = float(getattr(dyn, "dt", 0.05)), float(getattr(dyn, "max_torque", 2.0))
+    assert dt > 0 and maxu > 0
+    return (float(p[0]), float(p[1]), float(p[2]), dt, maxu)
 
 
 def _group_size(n, m):
