@@ -59,7 +59,7 @@ def measured_peaks():
 
 def ncu_traffic():
     """Measured DRAM bytes per solve of each kernel (one ncu --set full capture each, committed under profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r1", "traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2", "traffic.json")
     try:
         with open(path) as fh:
             return {k: v for k, v in json.load(fh).items() if not k.startswith("_")}
@@ -108,15 +108,18 @@ class ClockSampler:
 
 def elem_rel_err(a, b, floor_frac=1e-3):
     """Element-relative error with an absolute floor (same definition as tests/_helpers.rel_err): max over entries of
-    |a-b| / (|b| + floor), floor = floor_frac x the largest magnitude of the entry's own (timestep, element) block."""
+    |a-b| / (|b| + floor), floor = floor_frac x the largest magnitude of the entry's own (timestep, element) block (its
+    timestep when that block holds fewer than 8 numbers)."""
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     if b.size == 0:
         return 0.0
     ab = np.abs(b)
     gmax = float(np.max(ab))
-    if b.ndim >= 3:
+    if b.ndim >= 3 and int(np.prod(b.shape[2:])) >= 8:
         sl = np.max(ab, axis=tuple(range(2, b.ndim)), keepdims=True)
-    elif b.ndim == 2:
+    elif b.ndim >= 3:
+        sl = np.max(ab, axis=tuple(range(1, b.ndim)), keepdims=True)
+    elif b.ndim == 2 and b.shape[1] >= 8:
         sl = np.max(ab, axis=1, keepdims=True)
     else:
         sl = gmax
@@ -347,7 +350,7 @@ def run_b200(args):
         pr = make_problem_torch(torch, dev, n, m, T, Bc, seed=1234 + 1000 * rank + i)
         out = dict(x=torch.empty(T, Bc, n, dtype=f64, device=dev), u=torch.empty(T, Bc, m, dtype=f64, device=dev),
                    Ks=torch.empty(T, Bc, m, n, dtype=f64, device=dev), ks=torch.empty(T, Bc, m, dtype=f64, device=dev),
-                   fac=torch.empty(T, Bc, m * m + n * m, dtype=f64, device=dev),
+                   fac=torch.empty(ctx.lqr_fac_elems(T, Bc, n, m), dtype=f64, device=dev),
                    dx0=torch.empty(Bc, n, dtype=f64, device=dev), dC=torch.empty(T, Bc, s, s, dtype=f64, device=dev),
                    dc=torch.empty(T, Bc, s, dtype=f64, device=dev), dF=torch.empty(T - 1, Bc, n, s, dtype=f64, device=dev),
                    df=torch.empty(T - 1, Bc, n, dtype=f64, device=dev))
@@ -484,15 +487,20 @@ def run_b200(args):
         fwd_name = "lqr_factor_dmma_warp_kernel" if dmma else "lqr_solve_kernel"
         s_ = n + m
         dtau_b = 8 * (2 * (T - 1) * n * s_ + T * (m * m + n * m) + T * m * n + 2 * T * s_)        # F twice, factors, K, grads, d-tau
+        fused_adj = dmma          # n=32/m=8: two-sweep adjoint on the saved V_t, v_t (csrc/lqr_adjoint_fused.cuh)
+        k1 = "lqr_dtau_kernel<FUSED>" if fused_adj else "lqr_dtau_kernel"
+        k2 = "adjoint_fused_kernel" if fused_adj else "adjoint_out_kernel"
         kernels = {
             fwd_name: {"ms": kt["forward"], "launches_per_step": 1, "algorithmic_bytes": Bc * fwd_b,
                        "role": "Riccati sweep + rollout, one launch (factor-only %.3f ms, rollout-only %.3f ms)" % (kt["factor"], kt["rollout"])},
-            "lqr_dtau_kernel": {"ms": kt["dtau"], "launches_per_step": 1, "algorithmic_bytes": None,
-                                "role": "adjoint LQR solve with the saved factors (two sweeps); its bytes are internal to the "
-                                        "adjoint, so only measured traffic is reported"},
-            "adjoint_out_kernel": {"ms": kt["adjoint_out"], "launches_per_step": 1, "algorithmic_bytes": Bc * (tot_b - fwd_b),
-                                   "role": "lambda / d-lambda recursions + dC, dc, dF, df, dx0 (carries the adjoint's algorithmic "
-                                           "bytes; the pair takes %.3f ms)" % kt["adjoint"]}}
+            k1: {"ms": kt["dtau"], "launches_per_step": 1, "algorithmic_bytes": None,
+                 "role": ("adjoint sweep 1 (t down): k'_t, v'_t from the saved Quu^-1, Qxu" if fused_adj else
+                          "adjoint LQR solve with the saved factors (two sweeps)") + "; its bytes are internal to the adjoint, "
+                         "so only measured traffic is reported"},
+            k2: {"ms": kt["adjoint_out"], "launches_per_step": 1, "algorithmic_bytes": Bc * (tot_b - fwd_b),
+                 "role": ("adjoint sweep 2 (t up): d-tau rollout fused with lambda = V x + v, d-lambda = V dx + v' and " if fused_adj
+                          else "lambda / d-lambda recursions + ") + "dC, dc, dF, df, dx0 (carries the adjoint's algorithmic bytes; "
+                         "the pair takes %.3f ms)" % kt["adjoint"]}}
         extra_kernels = {"lqr_dtau_kernel+adjoint_out_kernel<REDUCE_TB>+reduce_partials_kernel": {
             "ms": kt["adjoint_reduced"], "role": "KKT adjoint with the (T,B)-sum of dC,dc,dF,df fused in (shared-parameter "
             "models; not part of the timed step, which materialises the full gradients as the reference does)"}}
@@ -500,7 +508,8 @@ def run_b200(args):
             if k["algorithmic_bytes"]:
                 k["achieved_gbs"] = k["algorithmic_bytes"] / (k["ms"] * 1e-3) / 1e9
                 k["hbm_frac"] = k["achieved_gbs"] / peak
-            k["traffic"] = Bc * traffic[name]["bytes_per_solve"] if (dmma and name in traffic) else None
+            tname = name.split("<")[0] + ("_fused1" if name.endswith("<FUSED>") else "")
+            k["traffic"] = Bc * traffic[tname]["bytes_per_solve"] if (dmma and tname in traffic) else None
             if k["traffic"]:
                 k["traffic_gbs"] = k["traffic"] / (k["ms"] * 1e-3) / 1e9
                 k["traffic_hbm_frac"] = k["traffic_gbs"] / peak
@@ -528,7 +537,7 @@ def run_b200(args):
                      "chunk_batch": Bc,
                      "whole_step_achieved_gbs": whole, "whole_step_hbm_frac": whole / peak,
                      "algorithmic_bytes_per_solve": {"fwd": fwd_b, "fwd_bwd": tot_b},
-                     "traffic_source": "ncu dram__bytes_read+write per solve x launch batch (profiles/r1/traffic.json)"})
+                     "traffic_source": "ncu dram__bytes_read+write per solve x launch batch (profiles/r2/traffic.json)"})
         line = {"metric": "lqr_fwd_bwd_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -1,5 +1,6 @@
 // extern "C" boundary of libdiffmpc_b200.so (declared in include/diffmpc_b200.h).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include "../../include/diffmpc_b200.h"
@@ -28,6 +29,18 @@ inline int cuda_fail(dmpc_handle h, cudaError_t e, const char* where) {
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, #call); } while (0)
 inline int set_dev(dmpc_handle h) { return cudaSetDevice(h->device) == cudaSuccess ? 0 : DMPC_ERR_CUDA; }
+// Shapes whose adjoint runs as two sweeps on the V_t, v_t saved by the forward (lqr_adjoint_fused.cuh).
+// DMPC_ADJ_UNFUSED=1 selects the three-sweep kernels for A/B runs.
+inline bool adjoint_fused_available(int n, int m) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("DMPC_ADJ_UNFUSED"); off = (e && e[0] == '1') ? 1 : 0; }
+  if (off) return false;
+#define X(N_, M_) if (n == N_ && m == M_) return true;
+  DMPC_FUSED_SHAPES(X)
+#undef X
+  return false;
+}
+inline size_t fac_elems_per_step(int n, int m) { return (size_t)(m * m + n * m); }
 }  // namespace
 
 template <typename R>
@@ -44,6 +57,7 @@ static int lqr_solve_impl(dmpc_handle h, int T, int B, int n, int m, const void*
   p.x0 = (const R*)x0; p.C = (const R*)C; p.c = (const R*)c; p.F = (const R*)F; p.f = (const R*)f;
   p.c_scale = R(1);
   p.x = (R*)x; p.u = (R*)u; p.Ks = (R*)Ks; p.ks = (R*)ks; p.fac = (R*)fac;
+  if ((p.flags & LQR_SAVE_FAC) && adjoint_fused_available(n, m)) p.Vsave = (R*)fac + (size_t)T * B * fac_elems_per_step(n, m);
   int rc = launch_lqr_solve<R>(p, st, &h->launches);
   if (rc) h->err = "lqr_solve launch failed";
   return rc;
@@ -55,10 +69,26 @@ static int lqr_adjoint_impl(dmpc_handle h, int T, int B, int n, int m, const voi
                             const void* fac, void* dx0, void* dC, void* dc, void* dF, void* df, int flags,
                             cudaStream_t st, void* partials = nullptr, void* sums = nullptr) {
   DtauParams<R> d;
+  memset(&d, 0, sizeof(d));
   d.T = T; d.B = B; d.n = n; d.m = m;
   d.F = (const R*)F; d.gx = (const R*)gx; d.gu = (const R*)gu; d.Ks = (const R*)Ks; d.fac = (const R*)fac;
   d.dc = (R*)dc;
   int rc = DMPC_OK;
+  if (!partials && df && adjoint_fused_available(n, m)) {
+    // two sweeps: v'_t is parked in the df output buffer (row t-1) and in dx0 (t = 0) between them
+    d.vp = (R*)df; d.dx0 = (R*)dx0;
+    AdjFusedParams<R> a;
+    memset(&a, 0, sizeof(a));
+    a.T = T; a.B = B; a.n = n; a.m = m;
+    a.flags = (flags & DMPC_ADJ_STRICT_REFERENCE) ? (ADJ_QUIRK_DC | ADJ_QUIRK_DF) : 0;
+    a.F = (const R*)F; a.Ks = (const R*)Ks; a.Vv = (const R*)fac + (size_t)T * B * fac_elems_per_step(n, m);
+    a.x = (const R*)x; a.u = (const R*)u; a.vp = (const R*)df; a.dx0 = (const R*)dx0;
+    a.dc = (R*)dc; a.dC = (R*)dC; a.dF = (R*)dF; a.df = (R*)df;
+    const int stage = (flags & DMPC_ADJ_STAGE_OUT_ONLY) ? 2 : ((flags & DMPC_ADJ_STAGE_DTAU_ONLY) ? 1 : 0);
+    rc = launch_adjoint_fused<R>(d, a, stage, st, &h->launches);
+    if (rc) h->err = "adjoint_fused launch failed";
+    return rc;
+  }
   if (!(flags & DMPC_ADJ_STAGE_OUT_ONLY)) {
     rc = launch_lqr_dtau<R>(d, st, &h->launches);
     if (rc) { h->err = "lqr_dtau launch failed"; return rc; }
@@ -364,7 +394,8 @@ int dmpc_sync(dmpc_handle h, void* stream) {
   return DMPC_OK;
 }
 
-size_t dmpc_lqr_fac_elems(int T, int B, int n, int m) { return (size_t)T * B * (size_t)(m * m + n * m); }
+// Quu^-1 | Qxu per (t,b), then V_t | v_t per (t,b) (the value function the two-sweep adjoint needs)
+size_t dmpc_lqr_fac_elems(int T, int B, int n, int m) { return (size_t)T * B * (size_t)(m * m + n * m + n * n + n); }
 
 int dmpc_lqr_solve(dmpc_handle h, int dtype, int T, int B, int n, int m, const void* d_x0, const void* d_C,
                    const void* d_c, const void* d_F, int F_T, const void* d_f, void* d_x, void* d_u, void* d_Ks,

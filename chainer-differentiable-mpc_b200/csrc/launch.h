@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "lqr_kernels.cuh"
+#include "lqr_adjoint_fused.cuh"
 
 namespace dmpc {
 
@@ -11,6 +12,10 @@ struct ShapeInfo { int n, m, G; bool specialised; };
 
 template <typename R> int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nlaunch);
 template <typename R> int launch_lqr_dtau(const DtauParams<R>& p, cudaStream_t st, long long* nlaunch);
+// two-sweep adjoint (lqr_adjoint_fused.cuh); DMPC_ERR_UNSUPPORTED when the shape has no instantiation
+#define DMPC_FUSED_SHAPES(X) X(32, 8)
+// stage: 0 = both sweeps, 1 = sweep 1 only, 2 = sweep 2 only (bench.py's per-kernel timing)
+template <typename R> int launch_adjoint_fused(const DtauParams<R>& d, const AdjFusedParams<R>& a, int stage, cudaStream_t st, long long* nlaunch);
 template <typename R> int launch_adjoint_out(const AdjOutParams<R>& p, cudaStream_t st, long long* nlaunch);
 template <typename R> int launch_reduce_partials(const R* red, int B, int rsz, R* out, cudaStream_t st, long long* nlaunch);
 

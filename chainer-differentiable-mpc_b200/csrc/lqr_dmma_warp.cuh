@@ -448,12 +448,16 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
 #pragma unroll
             for (int r = 0; r < 4; ++r) dmma(Qxx[r][c], Qxu[r][ee], b);
           }
+        IO* Vg = p.Vsave ? p.Vsave + idx * (N * N + N) : nullptr;     // V_t | v_t for the fused adjoint (lambda = V x + v)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const double vn = qx_s[r * 8 + gr] + quad_sum(__fma_rn(Qxu[r][0], kp.x, Qxu[r][1] * kp.y));
-          if (tg == 0) v_s[r * 8 + gr] = vn;
+          if (tg == 0) { v_s[r * 8 + gr] = vn; if (Vg) Vg[N * N + r * 8 + gr] = (IO)vn; }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { Vr[r][c][0] = Qxx[r][c][0]; Vr[r][c][1] = Qxx[r][c][1]; }
+          for (int c = 0; c < 4; ++c) {
+            Vr[r][c][0] = Qxx[r][c][0]; Vr[r][c][1] = Qxx[r][c][1];
+            if (Vg) st2(Vg + (r * 8 + gr) * N + c * 8 + 2 * tg, Vr[r][c][0], Vr[r][c][1]);
+          }
         }
       }
     }

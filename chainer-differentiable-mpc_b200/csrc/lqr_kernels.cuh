@@ -47,6 +47,7 @@ struct LqrParams {
   R* ks;         // [T,B,m]
   R* fac;        // [T,B,m*m + n*m]  (Quu^-1 | Qxu) or nullptr
   R* tau_out;    // [T,B,s] or nullptr: rollout also writes [x;u] concatenated
+  R* Vsave;      // [T,B,n*n+n] or nullptr: V_t | v_t of the Riccati sweep (t >= 1) for adjoint_fused_kernel
 };
 
 // shared-memory layout of one element's region for lqr_solve_kernel (offsets in reals)
@@ -223,6 +224,7 @@ __global__ void lqr_solve_kernel(LqrParams<R> p) {
             b += Rhs[l * ldr + i] * P[l * (n + 1) + j];
           }
           if (j < n) V[i * n + j] = a + b; else v[i] = a + b;
+          if (p.Vsave && valid) p.Vsave[((size_t)t * tb + e) * (n * n + n) + (j < n ? i * n + j : n * n + i)] = a + b;
         }
       }
       g.sync();
@@ -294,6 +296,8 @@ struct DtauParams {
   const R* Ks;   // [T,B,m,n]
   const R* fac;  // [T,B,m*m+n*m]
   R* dc;         // [T,B,s]  out: dtau
+  R* vp;         // FUSED: [T-1,B,n] out: v'_t for t >= 1 at row t-1 (the caller parks it in the df output buffer)
+  R* dx0;        // FUSED: [B,n] out: v'_0 = dlambda_0
 };
 
 struct DtauLayout { int oF, oA, oB, og, stage, st0, st1, q, vp, kp, dx, tmp, total, stride; };
@@ -323,7 +327,8 @@ __host__ __device__ inline DtauLayout dtau_layout(int n, int m) {
   return L;
 }
 
-template <typename R, int N, int M, int G>
+// FUSED = sweep 1 only, for adjoint_fused_kernel (lqr_adjoint_fused.cuh): also emits v'_t.
+template <typename R, int N, int M, int G, bool FUSED = false>
 __global__ void lqr_dtau_kernel(DtauParams<R> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = N > 0 ? N : p.n;
@@ -380,9 +385,14 @@ __global__ void lqr_dtau_kernel(DtauParams<R> p) {
       }
       if (valid) for (int o = g.lane; o < m; o += G) p.dc[((size_t)t * tb + e) * s + n + o] = kp[o];
       g.sync();
+      if (FUSED && valid) {
+        R* dst = t > 0 ? p.vp + ((size_t)(t - 1) * tb + e) * n : p.dx0 + (size_t)e * n;
+        for (int o = g.lane; o < n; o += G) dst[o] = vp[o];
+      }
       st ^= 1;
     }
   }
+  if (FUSED) return;
   // ---- sweep 2 (t = 0 .. T-1)
   {
     auto load_tiles = [&](int t, int st) {

@@ -99,7 +99,12 @@ static int launch_lqr_solve_dmma(const LqrParams<R>& p, cudaStream_t st, long lo
 template <typename R>
 int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
   const ShapeInfo si = pick_shape_impl(p.n, p.m);
-  if (p.n == 32 && p.m == 8 && !(p.flags & LQR_MASKED) && p.c && p.c_scale == R(1) && dmma_enabled())
+  // the DMMA kernel moves C, c, F, f, K_t, k_t with 16-byte cp.async / bulk copies and stores the factors with 16-byte
+  // stores: every such pointer must be 16-byte aligned (include/diffmpc_b200.h); otherwise the generic kernel (which
+  // checks alignment per copy) takes the call
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const bool aligned = al16(p.C) && al16(p.c) && al16(p.F) && al16(p.f) && al16(p.Ks) && al16(p.ks) && al16(p.fac) && al16(p.Vsave);
+  if (p.n == 32 && p.m == 8 && !(p.flags & LQR_MASKED) && p.c && p.c_scale == R(1) && dmma_enabled() && aligned)
     return launch_lqr_solve_dmma<R>(p, st, nl);
   const bool compact = !(p.flags & LQR_DO_FACTOR);
   const LqrLayout L = lqr_layout<R>(p.n, p.m, (p.flags & LQR_SAVE_FAC) != 0, compact);
@@ -130,6 +135,24 @@ int launch_lqr_dtau(const DtauParams<R>& p, cudaStream_t st, long long* nl) {
     case 32: return do_launch(lqr_dtau_kernel<R, 0, 0, 32>, p, 32, sb, p.B, st, nl);
     default: return do_launch(lqr_dtau_kernel<R, 0, 0, 64>, p, 64, sb, p.B, st, nl);
   }
+}
+
+// Two-sweep adjoint: sweep 1 (lqr_dtau_kernel<FUSED>) then adjoint_fused_kernel, one CTA per element each.
+
+template <typename R>
+int launch_adjoint_fused(const DtauParams<R>& d, const AdjFusedParams<R>& a, int stage, cudaStream_t st, long long* nl) {
+#define X(N_, M_)                                                                                                     \
+  if (d.n == N_ && d.m == M_) {                                                                                       \
+    const DtauLayout L1 = dtau_layout<R>(N_, M_);                                                                     \
+    int rc = DMPC_OK;                                                                                                 \
+    if (stage != 2) rc = do_launch(lqr_dtau_kernel<R, N_, M_, 64, true>, d, 64, (size_t)L1.stride * sizeof(R), d.B, st, nl); \
+    if (rc || stage == 1) return rc;                                                                                  \
+    const AdjFusedLayout L2 = adj_fused_layout<R>(N_, M_);                                                            \
+    return do_launch(adjoint_fused_kernel<R, N_, M_, 128>, a, 128, (size_t)L2.total * sizeof(R), a.B, st, nl);        \
+  }
+  DMPC_FUSED_SHAPES(X)
+#undef X
+  return DMPC_ERR_UNSUPPORTED;
 }
 
 template <typename R>
@@ -165,6 +188,7 @@ int launch_reduce_partials(const R* red, int B, int rsz, R* out, cudaStream_t st
 template int launch_reduce_partials<DMPC_REAL>(const DMPC_REAL*, int, int, DMPC_REAL*, cudaStream_t, long long*);
 template int launch_lqr_solve<DMPC_REAL>(const LqrParams<DMPC_REAL>&, cudaStream_t, long long*);
 template int launch_lqr_dtau<DMPC_REAL>(const DtauParams<DMPC_REAL>&, cudaStream_t, long long*);
+template int launch_adjoint_fused<DMPC_REAL>(const DtauParams<DMPC_REAL>&, const AdjFusedParams<DMPC_REAL>&, int, cudaStream_t, long long*);
 template int launch_adjoint_out<DMPC_REAL>(const AdjOutParams<DMPC_REAL>&, cudaStream_t, long long*);
 
 }  // namespace dmpc

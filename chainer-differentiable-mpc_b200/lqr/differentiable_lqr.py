@@ -46,7 +46,7 @@ class DiffLqr(FunctionNodeBase):
             T, B, n, m, s, dt, ctx = self.T, self.n_batch, self.n_state, self.n_ctrl, self.n_sc, self.dtype, self._ctx
             Tm = max(T - 1, 1)
             shapes = dict(x0=(B, n), C=(T, B, s, s), c=(T, B, s), F=(Tm, B, n, s), f=(Tm, B, n),
-                          x=(T, B, n), u=(T, B, m), Ks=(T, B, m, n), ks=(T, B, m), fac=(T, B, m * m + n * m),
+                          x=(T, B, n), u=(T, B, m), Ks=(T, B, m, n), ks=(T, B, m), fac=(ctx.lqr_fac_elems(T, B, n, m),),
                           gx=(T, B, n), gu=(T, B, m), dx0=(B, n), dC=(T, B, s, s), dc=(T, B, s),
                           dF=(Tm, B, n, s), df=(Tm, B, n))
             self._d = {k: ctx.empty(v, dt) for k, v in shapes.items()}

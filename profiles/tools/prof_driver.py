@@ -35,7 +35,7 @@ def main():
              gx=rs.randn(T, B, n), gu=rs.randn(T, B, m))
     dv = {k: ctx.to_device(v) for k, v in d.items()}
     o = dict(x=ctx.empty((T, B, n)), u=ctx.empty((T, B, m)), Ks=ctx.empty((T, B, m, n)), ks=ctx.empty((T, B, m)),
-             fac=ctx.empty((T, B, m * m + n * m)), dx0=ctx.empty((B, n)), dC=ctx.empty((T, B, s, s)),
+             fac=ctx.empty((ctx.lqr_fac_elems(T, B, n, m),)), dx0=ctx.empty((B, n)), dC=ctx.empty((T, B, s, s)),
              dc=ctx.empty((T, B, s)), dF=ctx.empty((T - 1, B, n, s)), df=ctx.empty((T - 1, B, n)))
     for _ in range(a.reps):
         ctx.lqr_solve(np.float64, T, B, n, m, dv["x0"], dv["C"], dv["c"], dv["F"], T - 1, dv["f"], o["x"], o["u"],

@@ -19,7 +19,7 @@ P = lambda t: t.data_ptr()
 def outputs(dt):
     return dict(x=torch.empty(T, B, n, dtype=dt, device=dev), u=torch.empty(T, B, m, dtype=dt, device=dev),
                 Ks=torch.empty(T, B, m, n, dtype=dt, device=dev), ks=torch.empty(T, B, m, dtype=dt, device=dev),
-                fac=torch.empty(T, B, m * m + n * m, dtype=dt, device=dev), dx0=torch.empty(B, n, dtype=dt, device=dev),
+                fac=torch.empty(ctx.lqr_fac_elems(T, B, n, m), dtype=dt, device=dev), dx0=torch.empty(B, n, dtype=dt, device=dev),
                 dC=torch.empty(T, B, s, s, dtype=dt, device=dev), dc=torch.empty(T, B, s, dtype=dt, device=dev),
                 dF=torch.empty(T - 1, B, n, s, dtype=dt, device=dev), df=torch.empty(T - 1, B, n, dtype=dt, device=dev))
 

@@ -12,7 +12,7 @@ pr = bench.make_problem_torch(torch, dev, n, m, T, B, seed=1)
 f64 = torch.float64
 o = dict(x=torch.empty(T, B, n, dtype=f64, device=dev), u=torch.empty(T, B, m, dtype=f64, device=dev),
          Ks=torch.empty(T, B, m, n, dtype=f64, device=dev), ks=torch.empty(T, B, m, dtype=f64, device=dev),
-         fac=torch.empty(T, B, m * m + n * m, dtype=f64, device=dev), dx0=torch.empty(B, n, dtype=f64, device=dev),
+         fac=torch.empty(ctx.lqr_fac_elems(T, B, n, m), dtype=f64, device=dev), dx0=torch.empty(B, n, dtype=f64, device=dev),
          dC=torch.empty(T, B, s, s, dtype=f64, device=dev), dc=torch.empty(T, B, s, dtype=f64, device=dev),
          dF=torch.empty(T - 1, B, n, s, dtype=f64, device=dev), df=torch.empty(T - 1, B, n, dtype=f64, device=dev))
 P = lambda t: t.data_ptr()

@@ -25,8 +25,10 @@ def rel_err_norm(a, b):
 def rel_err(a, b, floor_frac=None):
     """ELEMENT-relative error with an absolute floor: max over entries of |a-b| / (|b| + floor).
 
-    The floor of an entry is floor_frac x the largest magnitude of its own slice - one (timestep, batch element)
-    block for [T,B,...] tensors, one row for [B,k] - and never less than 1e-6 x the tensor-wide maximum.  A small late-
+    The floor of an entry is floor_frac x the largest magnitude of its own block - one (timestep, batch element)
+    block for [T,B,...] tensors whose trailing dims hold at least 8 numbers (gains, C, F, x at n >= 8), otherwise one
+    timestep (a [T,B,1] control has no block of its own to be relative to), one row for [B,k >= 8] - and never less than
+    1e-6 x the tensor-wide maximum.  A small late-
     horizon gain or a small gradient entry therefore has to be right relative to ITS block, not relative to the largest
     number anywhere in the tensor (the old tensor-wide norm let 1e-6-relative errors in small entries pass).
     floor_frac defaults to 1e-3 for float64 results and 3e-2 for float32 results (entries more than ~30x below their
@@ -41,9 +43,11 @@ def rel_err(a, b, floor_frac=None):
         return 0.0
     ab = np.abs(b)
     gmax = float(np.max(ab))
-    if b.ndim >= 3:
+    if b.ndim >= 3 and int(np.prod(b.shape[2:])) >= 8:
         sl = np.max(ab, axis=tuple(range(2, b.ndim)), keepdims=True)
-    elif b.ndim == 2:
+    elif b.ndim >= 3:
+        sl = np.max(ab, axis=tuple(range(1, b.ndim)), keepdims=True)
+    elif b.ndim == 2 and b.shape[1] >= 8:
         sl = np.max(ab, axis=1, keepdims=True)
     else:
         sl = gmax

@@ -51,6 +51,13 @@ def main(out_path):
             super().__init__(*a, **k)
             created.append(self)
     box_ddp.MPCstep = RecordingStep
+    solvers = []                                         # BoxDDP instances are local to the callers: record them
+    _fwd = box_ddp.BoxDDP.forward
+
+    def recording_forward(self, inputs):
+        solvers.append(self)
+        return _fwd(self, inputs)
+    box_ddp.BoxDDP.forward = recording_forward
 
     # ---------------------------------------------------------------- IL_Env.mpc (il_env.py:104-158, il_exp.py:249)
     g = load_golden("il_env_mpc")
@@ -67,12 +74,12 @@ def main(out_path):
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         xa, ua = env.mpc(env.true_dx, g["xinit"], V(g["q_true"]), V(g["p_true"]), update_dynamics=True)
-    res.update(xa=xa.array, ua=ua.array, log_a=buf.getvalue().strip().splitlines()[-1], n_iter_a=len(created) - 1)
+    res.update(xa=xa.array, ua=ua.array, log_a=buf.getvalue().strip().splitlines()[-1], n_iter_a=solvers[-1].info["n_iter"])
     del created[:]
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         xb, ub = env.mpc(env.true_dx, g["xinit"], V(g["q_l"]), V(g["p_l"]), u_init=g["warm"].copy())
-    res.update(xb=xb.array, ub=ub.array, log_b=buf.getvalue().strip().splitlines()[-1], n_iter_b=len(created) - 1)
+    res.update(xb=xb.array, ub=ub.array, log_b=buf.getvalue().strip().splitlines()[-1], n_iter_b=solvers[-1].info["n_iter"])
     final = created[-1]
     grads = final.backward((0, 1, 2, 3, 4), (None, V(g["gu"])))       # the FunctionNode protocol, full [T,B,...] tensors
     dC, dc = np.asarray(grads[1].array), np.asarray(grads[2].array)
@@ -105,7 +112,7 @@ def main(out_path):
     grads = final.backward((0, 1, 2, 3, 4), (V(g["gx"]), V(g["gu"])))
     red = final.backward_reduced_numpy(g["gx"], g["gu"])
     res.update(net_A=np.asarray(net.A.array), net_B=np.asarray(net.B.array), net_x=x.array, net_u=u.array,
-               net_costs=np.asarray(costs), net_log=buf.getvalue().strip().splitlines()[-1], net_n_iter=len(created) - 1,
+               net_costs=np.asarray(costs), net_log=buf.getvalue().strip().splitlines()[-1], net_n_iter=solvers[-1].info["n_iter"],
                net_dAB=np.asarray(grads[3].array).sum(axis=(0, 1)), net_dAB_red=red[3], net_dx0=np.asarray(grads[0].array))
     np.savez(out_path, **{k: np.asarray(v) for k, v in res.items()})
 

@@ -53,4 +53,4 @@ def test_every_entry_point_rejects_a_null_handle_without_touching_a_device():
     assert checked >= 18
     # the pure size queries need no handle state either
     assert lib.dmpc_reduced_grad_elems(32, 8) == 40 * 40 + 40 + 32 * 40 + 32
-    assert lib.dmpc_lqr_fac_elems(100, 4, 32, 8) == 100 * 4 * (8 * 8 + 32 * 8)
+    assert lib.dmpc_lqr_fac_elems(100, 4, 32, 8) == 100 * 4 * (8 * 8 + 32 * 8 + 32 * 32 + 32)      # Quu^-1 | Qxu | V | v

@@ -122,7 +122,9 @@ def test_boxddp_pendulum_like_il_env():
     # converged keep being iterated with steps |k| ~ 1e-8 whose cost change is below rounding, so the
     # accept/reject decision of the line search is noise in the reference itself (degenerate inputs,
     # see DESIGN.md §6); every non-degenerate decision matches and the result agrees to ~1e-6.
-    assert rel_err(arr(x), g["x"]) < 1e-5 and rel_err(arr(u), g["u"]) < 1e-5
+    # (tests/test_gpu_reference_callers.py::test_boxddp_pendulum_teacher_forced demonstrates that claim iteration by
+    # iteration; here the end result is compared in absolute terms: |u| <= 2, solver eps = 1e-3)
+    assert np.max(np.abs(arr(x) - g["x"])) < 1e-5 and np.max(np.abs(arr(u) - g["u"])) < 1e-5
     assert rel_err(costs, g["costs"]) < 1e-9
 
 

@@ -30,7 +30,7 @@ def run_solve(ctx, pr, dtype=np.float64, save_fac=True):
     df = None if f is None else ctx.to_device(f if f.size else np.zeros((1, B, n)), dtype)
     x = ctx.empty((T, B, n), dtype); u = ctx.empty((T, B, m), dtype)
     Ks = ctx.empty((T, B, m, n), dtype); ks = ctx.empty((T, B, m), dtype)
-    fac = ctx.empty((T, B, m * m + n * m), dtype) if save_fac else None
+    fac = ctx.empty((ctx.lqr_fac_elems(T, B, n, m),), dtype) if save_fac else None
     flags = _native.LQR_FACTOR | _native.LQR_ROLLOUT | (_native.LQR_SAVE_FAC if save_fac else 0)
     ctx.lqr_solve(dtype, T, B, n, m, d["x0"], d["C"], d["c"], dF, max(T - 1, F.shape[0]), df, x, u, Ks, ks, fac, flags)
     ctx.sync()

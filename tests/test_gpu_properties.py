@@ -19,7 +19,7 @@ def _solve(ctx, pr, flags=_native.LQR_FACTOR | _native.LQR_ROLLOUT | _native.LQR
     T, B, n, m = pr["T"], pr["B"], pr["n"], pr["m"]
     d = {k: ctx.to_device(pr[k]) for k in ("x0", "C", "c", "F", "f")}
     o = dict(x=ctx.empty((T, B, n)), u=ctx.empty((T, B, m)), Ks=ctx.empty((T, B, m, n)), ks=ctx.empty((T, B, m)),
-             fac=ctx.empty((T, B, m * m + n * m)))
+             fac=ctx.empty((ctx.lqr_fac_elems(T, B, n, m),)))
     ctx.lqr_solve(np.float64, T, B, n, m, d["x0"], d["C"], d["c"], d["F"], T - 1, d["f"], o["x"], o["u"], o["Ks"],
                   o["ks"], o["fac"], flags)
     ctx.sync()
