@@ -55,6 +55,7 @@ SIGNATURES = {
     "dmpc_mpc_step_backward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i] + [_vp] * 15 + [_vp]),
     "dmpc_lqr_active_solve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dmpc_get_traj": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(_d), _vp, _vp, _vp, _vp]),
+    "dmpc_expand_time_batch": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dmpc_reduced_grad_elems": (_sz, [_i, _i]),
     "dmpc_lqr_adjoint_reduced": (_i, [_vp, _i, _i, _i, _i, _i] + [_vp] * 13 + [_i, _vp]),
     "dmpc_mpc_step_backward_reduced": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i] + [_vp] * 13 + [_vp]),
@@ -67,7 +68,7 @@ SIGNATURES = {
 class BoxDdpOpts(ctypes.Structure):
     """dmpc_boxddp_opts of include/diffmpc_b200.h."""
     _fields_ = [("eps", _d), ("best_cost_eps", _d), ("ls_decay", _d), ("not_improved_lim", _i), ("max_iter", _i),
-                ("max_ls_trials", _i), ("coupling", _i)]
+                ("max_ls_trials", _i), ("coupling", _i), ("poll_every", _i)]
 
 
 BOXDDP_MAX_ITER, BOXDDP_CONVERGED, BOXDDP_NOT_IMPROVED = 0, 1, 2
@@ -171,8 +172,10 @@ class DeviceArray:
 class PackedBuffers:
     """Several typed device arrays carved from ONE allocation, so that a latency-bound call (a batch-64 MPC step
     moves a few hundred KB in ~20 tensors) needs one host->device and one device->host copy instead of one per
-    tensor.  `views[name]` are non-owning DeviceArrays; `upload(dict)` stages the host arrays contiguously and issues
-    one copy; `download()` returns host views of one copy."""
+    tensor.  `views[name]` are non-owning DeviceArrays; `upload(dict)` stages the host arrays contiguously in a PINNED
+    host buffer and issues one copy; `download()` returns copies of one device->host transfer.
+    `acquire(ctx, specs)` / `release()` keep one instance per layout in the context: a step that is called again and
+    again (BoxDDP's host loop, the latency benchmark) pays for the allocation and the page-locking once."""
 
     ALIGN = 256
 
@@ -188,27 +191,45 @@ class PackedBuffers:
             o = (o + nbytes + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.total = max(o, self.ALIGN)
         self.base = DeviceArray(ctx, (self.total,), np.uint8)
+        self.host = ctx.pinned_empty((self.total,), np.uint8)        # page-locked staging: copies run at PCIe speed
         self.views = {}
+        self._key = None
         for name, (off, shape, dt, nbytes) in self.layout.items():
             v = DeviceArray.__new__(DeviceArray)
             v.ctx, v.shape, v.dtype, v.nbytes, v.ptr, v._owned, v._base = ctx, shape, dt, nbytes, self.base.ptr + off, False, self.base
             self.views[name] = v
 
+    @classmethod
+    def acquire(cls, ctx, specs):
+        key = tuple((n, tuple(int(v) for v in sh), np.dtype(dt).str) for n, sh, dt in specs)
+        cache = ctx.__dict__.setdefault("_packed_cache", {})
+        lst = cache.get(key)
+        if lst:
+            return lst.pop()
+        pb = cls(ctx, specs)
+        pb._key = key
+        return pb
+
+    def release(self):
+        if self._key is None:
+            return self.free()
+        self.ctx.__dict__.setdefault("_packed_cache", {}).setdefault(self._key, []).append(self)
+
     def upload(self, arrays, stream=None):
-        host = np.empty(self.total, np.uint8)
+        host = self.host
         for name, arr in arrays.items():
             off, shape, dt, nbytes = self.layout[name]
-            a = np.ascontiguousarray(arr, dtype=dt)
+            a = np.asarray(arr)
             assert a.shape == shape, (name, a.shape, shape)
-            host[off:off + nbytes] = a.reshape(-1).view(np.uint8)
+            host[off:off + nbytes].view(dt).reshape(shape)[...] = a
         self.ctx._check(self.ctx.lib.dmpc_memcpy_h2d(self.ctx.h, self.base.ptr, host.ctypes.data, self.total, stream))
         return self.views
 
     def download(self, stream=None):
-        host = np.empty(self.total, np.uint8)
+        host = self.host
         self.ctx._check(self.ctx.lib.dmpc_memcpy_d2h(self.ctx.h, host.ctypes.data, self.base.ptr, self.total, stream))
         self.ctx.sync(stream)
-        return {name: host[off:off + nbytes].view(dt).reshape(shape) for name, (off, shape, dt, nbytes) in self.layout.items()}
+        return {name: host[off:off + nbytes].view(dt).reshape(shape).copy() for name, (off, shape, dt, nbytes) in self.layout.items()}
 
     def free(self):
         self.base.free()
@@ -388,18 +409,22 @@ class Context:
             self.h, dtype_code(dtype), T, B, n, m, _p(C), _p(c), _p(F), F_T, _p(x), _p(u), _p(lower), _p(upper),
             _p(gx), _p(gu), _p(ws_Ks), _p(ws_ks), _p(ws_dtau), _p(active), _p(ws_partials), _p(dx0), _p(sums), stream))
 
+    def expand_time_batch(self, dtype, T, B, src, dst, count, stream=None):
+        """dst[t,b,:] = src[:] on the device (util.expand_time_batch, reference util.py:361-377)."""
+        self._check(self.lib.dmpc_expand_time_batch(self.h, dtype_code(dtype), T, B, int(count), _p(src), _p(dst), stream))
+
     def reduced_grad_elems(self, n, m):
         return int(self.lib.dmpc_reduced_grad_elems(n, m))
 
     def boxddp_solve(self, dtype, T, B, n, m, x_init, C, c, lower, upper, dynamics, F, F_T, f, dyn_params, u_init,
                      eps, best_cost_eps, ls_decay, not_improved_lim, max_iter, max_ls_trials, coupling,
-                     x_best, u_best, costs_best, du_best, du_last, F_lin=None, f_lin=None, stream=None):
+                     x_best, u_best, costs_best, du_best, du_last, F_lin=None, f_lin=None, stream=None, poll_every=0):
         """Device-resident BoxDDP loop; returns (n_iter, status, flags)."""
         need = _sz(0)
         self._check(self.lib.dmpc_boxddp_workspace_bytes(dtype_code(dtype), T, B, n, m, ctypes.byref(need)))
         ws = DeviceArray(self, (int(need.value),), np.uint8)
         opts = BoxDdpOpts(float(eps), float(best_cost_eps), float(ls_decay), int(not_improved_lim), int(max_iter),
-                          int(max_ls_trials), int(coupling))
+                          int(max_ls_trials), int(coupling), int(poll_every))
         n_iter, status, flags = _i(0), _i(0), _i(0)
         try:
             self._check(self.lib.dmpc_boxddp_solve(

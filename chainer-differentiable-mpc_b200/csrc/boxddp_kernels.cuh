@@ -47,9 +47,38 @@ __device__ R np_pairwise_sum(const Fn& f, int lo, int n) {
   return add_rn(np_pairwise_sum<R>(f, lo, n2), np_pairwise_sum<R>(f, lo + n2, n - n2));
 }
 
+// Loop control that lives on the device, so that the host does not have to synchronise every iteration: after each
+// iteration boxddp_decide_kernel applies the reference's exit tests (box_ddp.py:184-230) to the reductions of
+// best_update_kernel and raises `done`; every kernel of a later iteration returns at once when it sees it.  The host
+// enqueues a few iterations at a time and reads this record once per block.
+struct BoxDdpCtl {
+  int done;              // 1 = an exit test fired (or a non-finite value was seen)
+  int status;            // DMPC_BOXDDP_MAX_ITER / _CONVERGED / _NOT_IMPROVED
+  int n_iter;            // iterations executed
+  int n_not_improved;    // the reference's shared counter (box_ddp.py:184, 203, 226)
+  int flags_or;          // OR of the per-element flags over all iterations
+  int nonfinite;
+  int pad[2];
+};
+
+__global__ void boxddp_decide_kernel(BoxDdpStatus* st, BoxDdpCtl* ctl, int iter, double eps, int not_improved_lim) {
+  if (ctl->done) return;
+  ctl->n_iter = iter + 1;
+  ctl->flags_or |= st->flags_or;
+  int nn = ctl->n_not_improved + 1;
+  if (iter > 0 && st->any_better) nn = 0;
+  ctl->n_not_improved = nn;
+  const double max_du = __longlong_as_double((long long)st->max_du_bits);
+  if (st->nonfinite) { ctl->nonfinite = 1; ctl->done = 1; }
+  else if (max_du < eps) { ctl->status = DMPC_BOXDDP_CONVERGED; ctl->done = 1; }                 // box_ddp.py:223-225
+  else if (nn > not_improved_lim) { ctl->status = DMPC_BOXDDP_NOT_IMPROVED; ctl->done = 1; }    // :227-229
+  st->any_better = 0; st->flags_or = 0; st->nonfinite = 0; st->max_du_bits = 0ull;               // next iteration's reductions
+}
+
 // out[r] = sqrt(sum_q d[q]^2), q in [r L, (r+1) L), L = T m, where d is (a - b)[T,B,m] read in [T,m,B] order
 template <typename R>
-__global__ void scrambled_norm_kernel(int T, int B, int m, const R* a, const R* b, R* out) {
+__global__ void scrambled_norm_kernel(int T, int B, int m, const R* a, const R* b, R* out, const int* skip) {
+  if (skip && *skip) return;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B) return;
   const int L = T * m;
@@ -69,7 +98,8 @@ __global__ void scrambled_norm_kernel(int T, int B, int m, const R* a, const R* 
 template <typename R>
 __global__ void best_update_kernel(int T, int B, int n, int m, int first, R best_cost_eps, const R* x, const R* u,
                                    const R* costs, const R* du, const int* flags, R* bx, R* bu, R* bcosts, R* bdu,
-                                   BoxDdpStatus* st) {
+                                   BoxDdpStatus* st, const int* skip) {
+  if (skip && *skip) return;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   int better = 0, fl = 0, bad = 0;
   unsigned long long dub = 0ull;

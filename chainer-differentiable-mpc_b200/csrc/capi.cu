@@ -119,7 +119,7 @@ static int mpc_forward_impl(dmpc_handle h, int T, int B, int n, int m, const voi
                             const void* tf, const double* dynp, double ls_decay, int max_ls_trials, int need_expand,
                             int coupling, void* x, void* u, void* Ks, void* ks, void* u_first, void* objs,
                             void* costs, void* old_costs, void* alphas, void* n_qp, void* free_m, void* n_ls,
-                            void* flags, cudaStream_t st) {
+                            void* flags, cudaStream_t st, const int* skip = nullptr) {
   MpcFwdParams<R> p;
   memset(&p, 0, sizeof(p));
   p.T = T; p.B = B; p.n = n; p.m = m; p.F_T = F_T; p.need_expand = need_expand; p.dynamics = dynamics;
@@ -131,7 +131,7 @@ static int mpc_forward_impl(dmpc_handle h, int T, int B, int n, int m, const voi
   for (int i = 0; i < 5; ++i) p.dyn_params[i] = dynp ? (R)dynp[i] : R(0);
   p.x = (R*)x; p.u = (R*)u; p.Ks = (R*)Ks; p.ks = (R*)ks; p.u_first = (R*)u_first; p.objs = (R*)objs;
   p.costs = (R*)costs; p.old_costs = (R*)old_costs; p.alphas = (R*)alphas; p.n_qp = (int*)n_qp;
-  p.free_mask = (unsigned char*)free_m; p.n_ls = (int*)n_ls; p.flags = (int*)flags;
+  p.free_mask = (unsigned char*)free_m; p.n_ls = (int*)n_ls; p.flags = (int*)flags; p.skip = skip;
   int rc = launch_mpc_forward<R>(p, st, &h->launches);
   if (rc) h->err = rc == DMPC_ERR_UNSUPPORTED ? "mpc_step_forward: unsupported shape / batch coupling needs the batch in one CTA" : "mpc_step_forward launch failed";
   return rc;
@@ -204,13 +204,14 @@ static int pnqp_impl(dmpc_handle h, int B, int m, const void* H, const void* q, 
 
 template <typename R>
 static int traj_impl(dmpc_handle h, int T, int B, int n, int m, int dynamics, const void* x0, const void* u,
-                     const void* F, const void* f, const double* dynp, void* x, void* Fo, void* fo, cudaStream_t st) {
+                     const void* F, const void* f, const double* dynp, void* x, void* Fo, void* fo, cudaStream_t st,
+                     const int* skip = nullptr) {
   TrajParams<R> p;
   memset(&p, 0, sizeof(p));
   p.T = T; p.B = B; p.n = n; p.m = m; p.dynamics = dynamics;
   p.x0 = (const R*)x0; p.u = (const R*)u; p.F = (const R*)F; p.f = (const R*)f;
   for (int i = 0; i < 5; ++i) p.dyn_params[i] = dynp ? (R)dynp[i] : R(0);
-  p.x = (R*)x; p.Fout = (R*)Fo; p.fout = (R*)fo;
+  p.x = (R*)x; p.Fout = (R*)Fo; p.fout = (R*)fo; p.skip = skip;
   int rc = launch_traj<R>(p, st, &h->launches);
   if (rc) h->err = "get_traj launch failed";
   return rc;
@@ -223,7 +224,7 @@ extern "C" int dmpc_get_traj(dmpc_handle, int, int, int, int, int, int, const vo
 // host reads one 32-byte status record to apply the reference's (batch-global) exit tests.
 namespace {
 struct BoxWs {
-  size_t x_nom, u_a, u_b, x_new, Ks, ks, u_first, objs, costs, old, alphas, du, n_qp, free_m, n_ls, flags, status, total;
+  size_t x_nom, u_a, u_b, x_new, Ks, ks, u_first, objs, costs, old, alphas, du, n_qp, free_m, n_ls, flags, status, ctl, total;
 };
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline BoxWs box_ws(size_t w, int T, int B, int n, int m) {
@@ -233,7 +234,7 @@ inline BoxWs box_ws(size_t w, int T, int B, int n, int m) {
   L.Ks = take(w * T * B * m * n); L.ks = take(w * T * B * m); L.u_first = take(w * T * B * m); L.objs = take(w * T * B);
   L.costs = take(w * B); L.old = take(w * B); L.alphas = take(w * B); L.du = take(w * B);
   L.n_qp = take(sizeof(int) * (size_t)T * B); L.free_m = take((size_t)T * B * m); L.n_ls = take(sizeof(int) * (size_t)B);
-  L.flags = take(sizeof(int) * (size_t)B); L.status = take(sizeof(BoxDdpStatus));
+  L.flags = take(sizeof(int) * (size_t)B); L.status = take(sizeof(BoxDdpStatus)); L.ctl = take(sizeof(BoxDdpCtl));
   L.total = o;
   return L;
 }
@@ -252,40 +253,43 @@ static int boxddp_impl(dmpc_handle h, int dtype, int T, int B, int n, int m, con
   R* costs = (R*)(w + L.costs); R* old = (R*)(w + L.old); R* alphas = (R*)(w + L.alphas); R* du = (R*)(w + L.du);
   int* n_qp = (int*)(w + L.n_qp); unsigned char* free_m = (unsigned char*)(w + L.free_m); int* n_ls = (int*)(w + L.n_ls);
   int* flags = (int*)(w + L.flags); BoxDdpStatus* dst = (BoxDdpStatus*)(w + L.status);
+  BoxDdpCtl* dctl = (BoxDdpCtl*)(w + L.ctl);
   const bool pend = dynamics == DMPC_DYN_PENDULUM;
   const size_t ub = sizeof(R) * (size_t)T * B * m;
   CK(cudaMemcpyAsync(u_cur, u_init, ub, cudaMemcpyDeviceToDevice, st));
-  int n_not_improved = 0, status = DMPC_BOXDDP_MAX_ITER, n_iter = 0, flags_or = 0;
+  CK(cudaMemsetAsync(dst, 0, sizeof(BoxDdpStatus), st));
+  CK(cudaMemsetAsync(dctl, 0, sizeof(BoxDdpCtl), st));
+  // The loop runs on the device: the exit tests are boxddp_decide_kernel's, later iterations see ctl->done and return at
+  // once, and the host only reads the control record once per block of `poll` enqueued iterations (no per-iteration sync).
+  const int poll = o->poll_every > 0 ? o->poll_every : 8;
   const int tpb = 128, grid = (B + tpb - 1) / tpb;
-  for (int i = 0; i < o->max_iter; ++i) {
-    n_iter = i + 1;
-    CK(cudaMemsetAsync(dst, 0, sizeof(BoxDdpStatus), st));
-    int rc = dmpc_get_traj(h, dtype, T, B, n, m, dynamics, x_init, u_cur, F, f, dynp, x_nom, pend ? F_lin : nullptr,
-                           pend ? f_lin : nullptr, st);
-    if (rc) return rc;
-    rc = dmpc_mpc_step_forward(h, dtype, T, B, n, m, C, c, pend ? F_lin : F, pend ? T - 1 : F_T, nullptr, x_nom, u_cur, lo, hi,
-                               C, c, dynamics, pend ? nullptr : F, pend ? nullptr : f, dynp, o->ls_decay, o->max_ls_trials,
-                               1, o->coupling, x_new, u_new, Ks, ks, u_first, objs, costs, old, alphas, n_qp, free_m, n_ls,
-                               flags, st);
-    if (rc) return rc;
-    scrambled_norm_kernel<R><<<grid, tpb, 0, st>>>(T, B, m, u_cur, u_first, du);
-    best_update_kernel<R><<<grid, tpb, 0, st>>>(T, B, n, m, i == 0, (R)o->best_cost_eps, x_new, u_new, costs, du, flags,
-                                                (R*)x_best, (R*)u_best, (R*)costs_best, (R*)du_best, dst);
-    h->launches += 2;
-    BoxDdpStatus hs;
-    CK(cudaMemcpyAsync(&hs, dst, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  const int* skip = &dctl->done;
+  BoxDdpCtl hc;
+  memset(&hc, 0, sizeof(hc));
+  for (int i0 = 0; i0 < o->max_iter && !hc.done; i0 += poll) {
+    const int i1 = i0 + poll < o->max_iter ? i0 + poll : o->max_iter;
+    for (int i = i0; i < i1; ++i) {
+      int rc = traj_impl<R>(h, T, B, n, m, dynamics, x_init, u_cur, F, f, dynp, x_nom, pend ? F_lin : nullptr,
+                            pend ? f_lin : nullptr, st, skip);
+      if (rc) return rc;
+      rc = mpc_forward_impl<R>(h, T, B, n, m, C, c, pend ? F_lin : F, pend ? T - 1 : F_T, nullptr, x_nom, u_cur, lo, hi, C, c,
+                               dynamics, pend ? nullptr : F, pend ? nullptr : f, dynp, o->ls_decay, o->max_ls_trials, 1,
+                               o->coupling, x_new, u_new, Ks, ks, u_first, objs, costs, old, alphas, n_qp, free_m, n_ls, flags,
+                               st, skip);
+      if (rc) return rc;
+      scrambled_norm_kernel<R><<<grid, tpb, 0, st>>>(T, B, m, u_cur, u_first, du, skip);
+      best_update_kernel<R><<<grid, tpb, 0, st>>>(T, B, n, m, i == 0, (R)o->best_cost_eps, x_new, u_new, costs, du, flags,
+                                                  (R*)x_best, (R*)u_best, (R*)costs_best, (R*)du_best, dst, skip);
+      boxddp_decide_kernel<<<1, 1, 0, st>>>(dst, dctl, i, o->eps, o->not_improved_lim);
+      h->launches += 3;
+      R* t_ = u_cur; u_cur = u_new; u_new = t_;                     // next nominal controls = this step's controls
+    }
+    CK(cudaMemcpyAsync(&hc, dctl, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    R* t_ = u_cur; u_cur = u_new; u_new = t_;                       // next nominal controls = this step's controls
-    flags_or |= hs.flags_or;
-    if (hs.nonfinite) { if (h_n_iter) *h_n_iter = n_iter; return fail(h, DMPC_ERR_NONFINITE, "boxddp: non-finite trajectory, cost or step norm"); }
-    n_not_improved += 1;
-    if (i > 0 && hs.any_better) n_not_improved = 0;
-    double max_du;
-    memcpy(&max_du, &hs.max_du_bits, sizeof(double));
-    if (max_du < o->eps) { status = DMPC_BOXDDP_CONVERGED; break; }       // box_ddp.py:223-225
-    if (n_not_improved > o->not_improved_lim) { status = DMPC_BOXDDP_NOT_IMPROVED; break; }   // :227-229
   }
+  const int n_iter = hc.n_iter, status = hc.done ? hc.status : DMPC_BOXDDP_MAX_ITER, flags_or = hc.flags_or;
+  if (hc.nonfinite) { if (h_n_iter) *h_n_iter = n_iter; return fail(h, DMPC_ERR_NONFINITE, "boxddp: non-finite trajectory, cost or step norm"); }
   if (du_last) CK(cudaMemcpyAsync(du_last, du, sizeof(R) * (size_t)B, cudaMemcpyDeviceToDevice, st));
   if (pend) {   // linearise at the returned point (box_ddp.py:235-242); the rollout itself is scratch
     int rc = dmpc_get_traj(h, dtype, T, B, n, m, dynamics, x_best, u_best, nullptr, nullptr, dynp, x_nom, F_lin, f_lin, st);
@@ -542,6 +546,18 @@ int dmpc_boxddp_solve(dmpc_handle h, int dtype, int T, int B, int n, int m, cons
   cudaStream_t st = pick(h, stream);
   if (dtype == DMPC_F64) return boxddp_impl<double>(h, dtype, T, B, n, m, d_x_init, d_C, d_c, d_lower, d_upper, dynamics, d_F, F_T, d_f, h_dyn_params, d_u_init, opts, d_ws, d_x_best, d_u_best, d_costs_best, d_du_best, d_du_last, d_F_lin, d_f_lin, h_n_iter, h_status, h_flags, st);
   return boxddp_impl<float>(h, dtype, T, B, n, m, d_x_init, d_C, d_c, d_lower, d_upper, dynamics, d_F, F_T, d_f, h_dyn_params, d_u_init, opts, d_ws, d_x_best, d_u_best, d_costs_best, d_du_best, d_du_last, d_F_lin, d_f_lin, h_n_iter, h_status, h_flags, st);
+}
+
+int dmpc_expand_time_batch(dmpc_handle h, int dtype, int T, int B, int count, const void* d_src, void* d_dst, void* stream) {
+  if (!h) return DMPC_ERR_NULL;
+  if (T < 1 || B < 1 || count < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "T,B,count must be >= 1");
+  if (!d_src || !d_dst) return fail(h, DMPC_ERR_NULL, "expand_time_batch: src/dst required");
+  if (set_dev(h)) return DMPC_ERR_CUDA;
+  cudaStream_t st = pick(h, stream);
+  const size_t total = (size_t)T * B * count;
+  if (dtype == DMPC_F64) return launch_expand_time_batch<double>((const double*)d_src, (double*)d_dst, count, total, st, &h->launches);
+  if (dtype == DMPC_F32) return launch_expand_time_batch<float>((const float*)d_src, (float*)d_dst, count, total, st, &h->launches);
+  return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
 }
 
 size_t dmpc_reduced_grad_elems(int n, int m) { return (size_t)adj_red_elems(n, m); }

@@ -143,23 +143,25 @@ __global__ void __launch_bounds__(G) adjoint_fused_kernel(AdjFusedParams<R> p) {
     // ---- D: gradients of step t (differentiable_lqr.py:128-134)
     const size_t idx = (size_t)t * tb + e;
     auto tau = [&](int j) -> R { return j < n ? xt[j] : ut[j - n]; };
-    {
-      R* dCg = p.dC + idx * s * s;
-      for (int o = g.lane; o < s * s; o += G) {
-        const int i = o / s, j = o - i * s;
-        const R a = dtau[i] * tau(j), b = tau(i) * dtau[j];
-        dCg[o] = quirk_dC ? (R(0.5) * a + b) : (R(0.5) * (a + b));
+    // thread (ti, tj) owns column tj of the rows ti, ti + NR, ...: tau_j, dtau_j stay in registers and the row operands
+    // are warp broadcasts (2 shared-memory reads per output instead of 4, no bank conflicts); rows are written whole
+    constexpr int NR = G / s;
+    static_assert(NR >= 1, "one column per thread");
+    const int tj = g.lane % s, ti = g.lane / s;
+    if (ti < NR) {
+      const R tau_j = tau(tj), dt_j = dtau[tj];
+      R* dCg = p.dC + idx * s * s + tj;
+      for (int i = ti; i < s; i += NR) {
+        const R a = dtau[i] * tau_j, b = tau(i) * dt_j;
+        dCg[i * s] = quirk_dC ? (R(0.5) * a + b) : (R(0.5) * (a + b));
       }
-      for (int o = g.lane; o < s; o += G) p.dc[idx * s + o] = dtau[o];
-    }
-    if (more) {
-      R* dFg = p.dF + idx * n * s;
-      for (int o = g.lane; o < n * s; o += G) {
-        const int i = o / s, j = o - i * s;
-        dFg[o] = dlam[i] * tau(j) + lam[i] * dtau[j];
+      if (more) {
+        R* dFg = p.dF + idx * n * s + tj;
+        for (int i = ti; i < n; i += NR) dFg[i * s] = dlam[i] * tau_j + lam[i] * dt_j;
       }
-      if (p.df) for (int o = g.lane; o < n; o += G) p.df[idx * n + o] = quirk_df ? dlamp[o] : dlam[o];
     }
+    for (int o = g.lane; o < s; o += G) p.dc[idx * s + o] = dtau[o];
+    if (more && p.df) for (int o = g.lane; o < n; o += G) p.df[idx * n + o] = quirk_df ? dlamp[o] : dlam[o];
     g.sync();
     if (more) for (int o = g.lane; o < n; o += G) { dtau[o] = dxn[o]; dlamp[o] = dlam[o]; }
     g.sync();

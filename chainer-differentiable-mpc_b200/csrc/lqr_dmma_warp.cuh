@@ -1,9 +1,9 @@
 // Large-state Riccati sweep, second generation: ONE WARP owns one batch element and keeps the whole
 // recursion state in DMMA fragment registers (sm_100a, mma.sync.m8n8k4.f64).
 //
-// Why: the CTA-per-element kernel (lqr_dmma.cuh) fetches every DMMA operand from shared memory and is bound
-// by the shared-memory pipe (ncu r1f: l1tex data-pipe wavefronts 70 % of peak, 2995 wavefronts per
-// element-step against 1600 DMMA-pipe cycles).  Here the operands stay in registers:
+// Why: a CTA-per-element kernel that fetches every DMMA operand from shared memory (round 1's first generation,
+// profiles/r1/r1f_factor_cta_full.summary.txt) is bound by the shared-memory pipe (l1tex data-pipe wavefronts 70 % of
+// peak, 2995 wavefronts per element-step against 1600 DMMA-pipe cycles).  Here the operands stay in registers:
 //
 //   * the accumulator layout of a DMMA output tile (lane (g,t) holds D[g][2t], D[g][2t+1]) IS a valid
 //     B (or A) fragment of the next product if the contraction index inside each 8-block is enumerated
@@ -26,7 +26,6 @@
 #pragma once
 #include "common.cuh"
 #include "lqr_kernels.cuh"
-#include "lqr_dmma.cuh"
 
 namespace dmpc {
 
@@ -42,7 +41,10 @@ __device__ __forceinline__ double quad_sum(double a) {      // sum over the 4 la
   return a;
 }
 
-// One pivot step of the Gauss-Jordan inverse (see warp_gj_inverse in lqr_dmma.cuh), branch-free so that the
+__device__ __forceinline__ unsigned abs_hi(double x) { return (unsigned)__double2hiint(x) & 0x7fffffffu; }   // |x| high word
+
+// One pivot step of the in-register Gauss-Jordan inverse of Quu (lanes 0..7 hold the columns of Quu, lanes 8..15 the
+// columns of I; afterwards lanes 8..15 hold the columns of Quu^-1), branch-free so that the
 // compiler can interleave it with the independent DMMA stream of the Q passes.
 // 1/x to ~1 ulp: MUFU seed (20 bits), one Newton step (40 bits), one correction in residual form
 __device__ __forceinline__ double fast_rcp2(double x) {
@@ -96,31 +98,6 @@ template <> __device__ __forceinline__ double2 ld2<float>(const float* p) {
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 __device__ __forceinline__ void st2(float* p, double a, double b) { *reinterpret_cast<float2*>(p) = make_float2((float)a, (float)b); }
 
-#ifdef DMPC_GJ_FASTPATH
-// EXPERIMENT (off by default; build with `make EXTRA=-DDMPC_GJ_FASTPATH`): pivot-free Gauss-Jordan step with an acceptance
-// test, for the next round's A/B.  The static mix (profiles/r1/sass_mix_factor_warp.txt) shows the pivoted inverse is a
-// third of the sweep's instruction stream.  Quu has a positive-definite symmetric part in every BASELINE workload, where
-// elimination without row exchanges is stable; `bad` is raised when a pivot is smaller than 2^-6 of the largest entry
-// below it (compared on the high word), and the caller then redoes the inverse with the pivoted steps.  Every lane sees
-// the same broadcast column, so `bad` is warp uniform.
-template <int M>
-__device__ __forceinline__ void gj_step_nopivot(double (&c)[M], const int k, unsigned& bad) {
-  constexpr unsigned FULL = 0xffffffffu;
-  double pc[M];
-#pragma unroll
-  for (int i = 0; i < M; ++i) pc[i] = __shfl_sync(FULL, c[i], k);
-  unsigned mx = 0u;
-#pragma unroll
-  for (int i = 0; i < M; ++i)
-    if (i > k) mx = max(mx, abs_hi(pc[i]));
-  bad |= (abs_hi(pc[k]) + (6u << 20) < mx) ? 1u : 0u;
-  const double ck = c[k] * fast_rcp2(pc[k]);
-  c[k] = ck;
-#pragma unroll
-  for (int i = 0; i < M; ++i)
-    if (i != k) c[i] = __fma_rn(-pc[i], ck, c[i]);
-}
-#endif
 
 struct WarpCfg {
   static constexpr int N = 32, M = 8, S = 40;
@@ -136,11 +113,7 @@ struct WarpCfg {
   static constexpr int LDK = 34;     // K panel [8][34]: B fragments by rows 2t+e (aliases the Qux panel)
   static constexpr int OQux = OSCR, OK = OQux, OQuu = OQux + M * LDQ, OQi = OQuu + M * LDU, Oqu = OQi + M * LDU,
                        Okk = Oqu + M, Omv = Okk + M, Obar = Omv + N;                     // two mbarriers per warp
-#ifdef DMPC_GJ_FASTPATH
-  static constexpr int Oqx = Obar + 2, TOTAL = Oqx + N;   // q_x gets its own slot: the Quu panel must survive for the fallback
-#else
   static constexpr int TOTAL = Obar + 2;
-#endif
   // rollout: two stages {F, f, K_t [8][36], k_t} carved from the same region, then x|u and x_next
   static constexpr int LDKR = 36;
   static constexpr int RF = 0, Rf = RF + N * LDF, RK = Rf + N, Rk = RK + M * LDKR, RSTG = Rk + M;
@@ -200,7 +173,7 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
   const int gr = lane >> 2, tg = lane & 3;
   const int T = p.T, B = p.B;
   const int e = blockIdx.x * WPC + warp;
-  if (e >= B) return;                       // warps are independent: no CTA-wide barrier anywhere below
+  if (e >= B) return;                       // warps never synchronise CTA-wide below this point
   double* sm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * Cfg::TOTAL;
   const size_t tb = (size_t)B;
   const bool have_f = p.f != nullptr;
@@ -243,12 +216,7 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
     // V_t as accumulator-layout registers: Vr[r][kb][e] = V[8r+g][8kb+2t+e];  vr[r] = v[8r+g]
     // v_t and q_x live in shared memory between their producer and consumer (v aliases mv, q_x aliases Quu)
     double Vr[4][4][2];
-#ifdef DMPC_GJ_FASTPATH
-    double* v_s = mv_s; double* qx_s = sm + Cfg::Oqx;
-    unsigned gj_bad = 0u;
-#else
     double* v_s = mv_s; double* qx_s = Quu_s;
-#endif
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
 #pragma unroll
@@ -272,21 +240,26 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
 
       double WT[5][4][2];          // WT[j][r][e] = W[8r+2t+e][8j+g],  W = V F
       if (!last) {
-        // ---- mv = V f + v
+        // ---- mv = V f + v.  V f is a DMMA product too (B operand = f in column 0, zero elsewhere): a scalar DFMA issued
+        //      while the other warp of the sub-partition streams DMMAs waits for the FP64 pipe as long as a DMMA does
+        //      (profiles/r2/fwd_pass_stalls.txt), and its shuffle reduction adds a dependent chain on top
         double mvr[4];
+        if (have_f) {
+          double mvt[4][2];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          double a = 0.0;
-          if (have_f) {
+          for (int r = 0; r < 4; ++r) { mvt[r][0] = 0.0; mvt[r][1] = 0.0; }
 #pragma unroll
-            for (int kb = 0; kb < 4; ++kb) {
-              const double2 f2 = ld2<IO>(fs + kb * 8 + 2 * tg);
-              a = __fma_rn(Vr[r][kb][0], f2.x, a);
-              a = __fma_rn(Vr[r][kb][1], f2.y, a);
-            }
-            a = quad_sum(a);
+          for (int kb = 0; kb < 4; ++kb) {
+            const double2 f2 = ld2<IO>(fs + kb * 8 + 2 * tg);
+            const double b0 = (gr == 0) ? f2.x : 0.0, b1 = (gr == 0) ? f2.y : 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { dmma(mvt[r], Vr[r][kb][0], b0); dmma(mvt[r], Vr[r][kb][1], b1); }
           }
-          mvr[r] = a + v_s[r * 8 + gr];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) mvr[r] = mvt[r][0] + v_s[r * 8 + gr];      // lanes t = 0 hold column 0
+        } else {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) mvr[r] = v_s[r * 8 + gr];
         }
         __syncwarp();                                  // every lane has read v before mv overwrites it
         if (tg == 0) {
@@ -314,10 +287,11 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
         __syncwarp();                                  // mv_s complete
       }
 
-      // ---- Q = C + F^T W (row block u first), q = c + F^T mv.  The Gauss-Jordan inverse of Quu (available after
-      //      the first pass) is interleaved with the DMMAs of the next two passes: 8 pivot steps, one per two k-steps.
+      // ---- Q = C + F^T W, row block u first; q = c + F^T mv rides along as a sixth accumulator tile whose B operand is
+      //      mv in column 0 (8 extra DMMAs per pass instead of 8 DFMAs + 2 shuffles per lane that would each wait for the
+      //      FP64 pipe).  After the first pass the Gauss-Jordan inverse of Quu, K = -Quu^-1 Qux and k = -Quu^-1 qu run as
+      //      one scalar section; the four Qxx passes that follow are pure DMMA streams.
       double Qxx[4][4][2], Qxu[4][2];
-      double cinv[M];
       IO* fg = save_fac ? p.fac + idx * (M * M + N * M) : nullptr;
 #pragma unroll
       for (int pi = 0; pi < 5; ++pi) {
@@ -338,11 +312,39 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
           stage_C_rows(t - 1, i);
         }
         if (pi == 1) {
+          double cinv[M];
 #pragma unroll
           for (int ii = 0; ii < M; ++ii) cinv[ii] = (lane < M) ? Quu_s[ii * LDU + lane] : ((lane - M == ii) ? 1.0 : 0.0);
-          __syncwarp();                                // q_x (stored at the end of this pass) aliases the Quu panel
+#pragma unroll
+          for (int k = 0; k < M; ++k) gj_step<M>(cinv, k);
+          if (lane >= M && lane < 2 * M) {             // lanes 8..15 hold the columns of Quu^-1
+#pragma unroll
+            for (int ii = 0; ii < M; ++ii) { Qi_s[ii * LDU + lane - M] = cinv[ii]; if (fg) fg[ii * M + lane - M] = (IO)cinv[ii]; }
+          }
+          __syncwarp();                                // Quu^-1 complete (q_x, stored by the passes below, aliases the Quu panel)
+          double Kt[4][2];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { Kt[c][0] = 0.0; Kt[c][1] = 0.0; }
+#pragma unroll
+          for (int k0 = 0; k0 < M; k0 += 4) {
+            const double a = Qi_s[gr * LDU + k0 + tg];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dmma(Kt[c], a, Qux_s[(k0 + tg) * LDQ + c * 8 + gr]);
+          }
+          const double2 qi2 = *reinterpret_cast<const double2*>(Qi_s + gr * LDU + 2 * tg);
+          const double2 qu2 = *reinterpret_cast<const double2*>(qu_s + 2 * tg);
+          const double kk = -quad_sum(__fma_rn(qi2.x, qu2.x, qi2.y * qu2.y));
+          if (tg == 0) { kk_s[gr] = kk; p.ks[idx * M + gr] = (IO)kk; }
+          __syncwarp();                                // every lane has read the Qux panel: K may overwrite it
+          IO* Kg = p.Ks + idx * (M * N) + gr * N + 2 * tg;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double2 k2 = make_double2(-Kt[c][0], -Kt[c][1]);
+            *reinterpret_cast<double2*>(K_s + gr * LDK + c * 8 + 2 * tg) = k2;
+            st2(Kg + c * 8, k2.x, k2.y);
+          }
         }
-        double qa = 0.0;
+        double acc5[2] = {0.0, 0.0};
         if (!last) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
@@ -352,84 +354,27 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
               const double a = Fs[(r * 8 + 2 * tg + ee) * LDF + i * 8 + gr];
 #pragma unroll
               for (int j = 0; j < 5; ++j) dmma(acc[j], a, WT[j][r][ee]);
-              qa = __fma_rn(a, ee ? m2.y : m2.x, qa);
-#ifdef DMPC_GJ_FASTPATH
-              if ((pi == 1 || pi == 2) && ee == 1) gj_step_nopivot<M>(cinv, (pi - 1) * 4 + r, gj_bad);
-#else
-              if ((pi == 1 || pi == 2) && ee == 1) gj_step<M>(cinv, (pi - 1) * 4 + r);
-#endif
+              dmma(acc5, a, (gr == 0) ? (ee ? m2.y : m2.x) : 0.0);
             }
           }
-          qa = quad_sum(qa);
-        } else if (pi == 1 || pi == 2) {
-#pragma unroll
-#ifdef DMPC_GJ_FASTPATH
-          for (int r = 0; r < 4; ++r) gj_step_nopivot<M>(cinv, (pi - 1) * 4 + r, gj_bad);
-#else
-          for (int r = 0; r < 4; ++r) gj_step<M>(cinv, (pi - 1) * 4 + r);
-#endif
         }
-#ifdef DMPC_GJ_FASTPATH
-        if (pi == 2 && gj_bad) {                       // rare, warp uniform: redo the inverse with row exchanges
-#pragma unroll
-          for (int ii = 0; ii < M; ++ii) cinv[ii] = (lane < M) ? Quu_s[ii * LDU + lane] : ((lane - M == ii) ? 1.0 : 0.0);
-#pragma unroll 1
-          for (int k = 0; k < M; ++k) {
-            switch (k) {                               // gj_step needs a compile-time row index
-              case 0: gj_step<M>(cinv, 0); break; case 1: gj_step<M>(cinv, 1); break;
-              case 2: gj_step<M>(cinv, 2); break; case 3: gj_step<M>(cinv, 3); break;
-              case 4: gj_step<M>(cinv, 4); break; case 5: gj_step<M>(cinv, 5); break;
-              case 6: gj_step<M>(cinv, 6); break; default: gj_step<M>(cinv, 7); break;
-            }
-          }
-          gj_bad = 0u;
-        }
-#endif
-        qa += cs[i * 8 + gr];
+        const double qa = acc5[0] + (double)cs[i * 8 + gr];          // lanes t = 0 hold column 0 of the sixth tile
         if (i == 4) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<double2*>(Qux_s + gr * LDQ + j * 8 + 2 * tg) = make_double2(acc[j][0], acc[j][1]);
           *reinterpret_cast<double2*>(Quu_s + gr * LDU + 2 * tg) = make_double2(acc[4][0], acc[4][1]);
           if (tg == 0) qu_s[gr] = qa;
+          __syncwarp();                                // the Qux | Quu | qu panels are complete
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) { Qxx[i][j][0] = acc[j][0]; Qxx[i][j][1] = acc[j][1]; }
           Qxu[i][0] = acc[4][0]; Qxu[i][1] = acc[4][1];
           if (tg == 0) qx_s[i * 8 + gr] = qa;
         }
-        if (pi == 2 && lane >= M && lane < 2 * M) {    // lanes 8..15 hold the columns of Quu^-1
-#pragma unroll
-          for (int ii = 0; ii < M; ++ii) { Qi_s[ii * LDU + lane - M] = cinv[ii]; if (fg) fg[ii * M + lane - M] = (IO)cinv[ii]; }
-        }
       }
-      __syncwarp();                                    // F_t, f_t, c_t, mv are dead; Qux, Quu^-1, qu are complete
+      __syncwarp();                                    // F_t, f_t, c_t, mv are dead; K, k, q_x are complete
       if (t > 0) stage_Ffc(t - 1);
-      __syncwarp();
-      // ---- K = -Quu^-1 Qux, k = -Quu^-1 qu
-      {
-        double Kt[4][2];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { Kt[c][0] = 0.0; Kt[c][1] = 0.0; }
-#pragma unroll
-        for (int k0 = 0; k0 < M; k0 += 4) {
-          const double a = Qi_s[gr * LDU + k0 + tg];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) dmma(Kt[c], a, Qux_s[(k0 + tg) * LDQ + c * 8 + gr]);
-        }
-        const double2 qi2 = *reinterpret_cast<const double2*>(Qi_s + gr * LDU + 2 * tg);
-        const double2 qu2 = *reinterpret_cast<const double2*>(qu_s + 2 * tg);
-        const double kk = -quad_sum(__fma_rn(qi2.x, qu2.x, qi2.y * qu2.y));
-        if (tg == 0) { kk_s[gr] = kk; p.ks[idx * M + gr] = (IO)kk; }
-        __syncwarp();                                  // every lane has read the Qux panel: K may overwrite it
-        IO* Kg = p.Ks + idx * (M * N) + gr * N + 2 * tg;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double2 k2 = make_double2(-Kt[c][0], -Kt[c][1]);
-          *reinterpret_cast<double2*>(K_s + gr * LDK + c * 8 + 2 * tg) = k2;
-          st2(Kg + c * 8, k2.x, k2.y);
-        }
-      }
       if (fg) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -449,9 +394,18 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
             for (int r = 0; r < 4; ++r) dmma(Qxx[r][c], Qxu[r][ee], b);
           }
         IO* Vg = p.Vsave ? p.Vsave + idx * (N * N + N) : nullptr;     // V_t | v_t for the fused adjoint (lambda = V x + v)
+        double vacc[4][2];                            // v = qx + Qxu k as a fifth column tile (B operand = k in column 0)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { vacc[r][0] = 0.0; vacc[r][1] = 0.0; }
+#pragma unroll
+        for (int ee = 0; ee < 2; ++ee) {
+          const double b5 = (gr == 0) ? (ee ? kp.y : kp.x) : 0.0;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) dmma(vacc[r], Qxu[r][ee], b5);
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const double vn = qx_s[r * 8 + gr] + quad_sum(__fma_rn(Qxu[r][0], kp.x, Qxu[r][1] * kp.y));
+          const double vn = qx_s[r * 8 + gr] + vacc[r][0];
           if (tg == 0) { v_s[r * 8 + gr] = vn; if (Vg) Vg[N * N + r * 8 + gr] = (IO)vn; }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {

@@ -642,6 +642,15 @@ __global__ void adjoint_out_kernel(AdjOutParams<R> p) {
   }
 }
 
+// util.expand_time_batch on the device (reference util.py:361-377): dst[t][b][:] = src[:] for a parameter block shared
+// by every (t, b) - the forward half of the shared-parameter entry (LqrNet, MpcNet_dx, IL_Env.mpc broadcast n*s or 2*n_sc
+// doubles over [T,B]); its backward is the fused (T,B)-sum of ADJ_REDUCE_TB.
+template <typename R>
+__global__ void expand_time_batch_kernel(const R* __restrict__ src, R* __restrict__ dst, int count, size_t total) {
+  for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x)
+    dst[o] = src[o % count];
+}
+
 // Second stage of ADJ_REDUCE_TB: out[o] = sum_e red[e][o] in a fixed order (lane-strided partial sums, then a
 // shuffle tree) - deterministic, unlike atomics.  One warp per output element.
 template <typename R>

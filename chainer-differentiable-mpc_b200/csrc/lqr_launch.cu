@@ -2,8 +2,6 @@
 #include <cstdlib>
 #include <type_traits>
 #include "launch.h"
-#include "lqr_dmma.cuh"
-#include "lqr_dmma_warp.cuh"
 
 #ifndef DMPC_REAL
 #define DMPC_REAL double
@@ -47,53 +45,12 @@ static bool dmma_enabled() {
   return v == 1;
 }
 
-static bool dmma_cta_kernel() {        // DMPC_DMMA_CTA=1: first-generation CTA-per-element kernel (A/B runs)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DMPC_DMMA_CTA"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
-// n=32, m=8: Riccati sweep on DMMA.  Default = warp-per-element register-resident kernel
-// (lqr_dmma_warp.cuh, rollout fused in); rollout-only calls use a compact launch of the generic kernel.
-// R = float: the same kernel with float tensors in HBM and in the staging buffers, fp64 arithmetic.
 template <typename R>
-static int launch_lqr_solve_dmma(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
-  constexpr bool F64 = std::is_same<R, double>::value;
-  if ((p.flags & LQR_DO_FACTOR) && !(F64 && dmma_cta_kernel())) {
-    constexpr int WPC = 4;
-    const size_t smem = (size_t)WPC * WarpCfg::TOTAL * sizeof(double);
-    auto kern = lqr_factor_dmma_warp_kernel<WPC, R>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DMPC_ERR_CUDA;
-    kern<<<(p.B + WPC - 1) / WPC, WPC * 32, smem, st>>>(p);
-    if (nl) ++*nl;
-    return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
-  }
-  if constexpr (F64) if (p.flags & LQR_DO_FACTOR) {
-    using Cfg = DmmaCfg<32, 8>;
-    const size_t smem = (size_t)Cfg::TOTAL * sizeof(double);
-    auto kern = lqr_factor_dmma_kernel<32, 8>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DMPC_ERR_CUDA;
-    static int n_sm = 0;
-    if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-    // default: one CTA per element (the hardware back-fills 3 CTAs per SM).  DMPC_FACTOR_CTAS_PER_SM=k makes
-    // the grid persistent with k CTAs per SM striding over the batch (k=2 leaves shared memory for a
-    // co-running kernel; measured slower on its own).
-    int grid = p.B;
-    if (const char* e = getenv("DMPC_FACTOR_CTAS_PER_SM")) {
-      const int v = atoi(e);
-      if (v >= 1 && v <= 3 && p.B > v * n_sm) grid = v * n_sm;
-    }
-    kern<<<grid, Cfg::NT, smem, st>>>(p);          // persistent CTAs; the rollout (if requested) is fused in
-    if (nl) ++*nl;
-    return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
-  }
-  if (p.flags & LQR_DO_ROLLOUT) {
-    LqrParams<R> q = p;
-    q.flags = LQR_DO_ROLLOUT;
-    const LqrLayout L = lqr_layout<R>(q.n, q.m, false, true);
-    return do_launch(lqr_solve_kernel<R, 32, 8, 32>, q, 32, (size_t)L.stride * sizeof(R), q.B, st, nl);
-  }
-  return DMPC_OK;
+int launch_lqr_rollout_32_8(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
+  LqrParams<R> q = p;
+  q.flags = LQR_DO_ROLLOUT;
+  const LqrLayout L = lqr_layout<R>(q.n, q.m, false, true);
+  return do_launch(lqr_solve_kernel<R, 32, 8, 32>, q, 32, (size_t)L.stride * sizeof(R), q.B, st, nl);
 }
 
 template <typename R>
@@ -185,7 +142,19 @@ int launch_reduce_partials(const R* red, int B, int rsz, R* out, cudaStream_t st
   return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
 }
 
+template <typename R>
+int launch_expand_time_batch(const R* src, R* dst, int count, size_t total, cudaStream_t st, long long* nl) {
+  const int tpb = 256;
+  size_t blocks = (total + tpb - 1) / tpb;
+  if (blocks > 148 * 32) blocks = 148 * 32;               // grid-stride: 32 CTAs per SM keep the store queues full
+  expand_time_batch_kernel<R><<<(unsigned)blocks, tpb, 0, st>>>(src, dst, count, total);
+  if (nl) ++*nl;
+  return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+}
+
+template int launch_expand_time_batch<DMPC_REAL>(const DMPC_REAL*, DMPC_REAL*, int, size_t, cudaStream_t, long long*);
 template int launch_reduce_partials<DMPC_REAL>(const DMPC_REAL*, int, int, DMPC_REAL*, cudaStream_t, long long*);
+template int launch_lqr_rollout_32_8<DMPC_REAL>(const LqrParams<DMPC_REAL>&, cudaStream_t, long long*);
 template int launch_lqr_solve<DMPC_REAL>(const LqrParams<DMPC_REAL>&, cudaStream_t, long long*);
 template int launch_lqr_dtau<DMPC_REAL>(const DtauParams<DMPC_REAL>&, cudaStream_t, long long*);
 template int launch_adjoint_fused<DMPC_REAL>(const DtauParams<DMPC_REAL>&, const AdjFusedParams<DMPC_REAL>&, int, cudaStream_t, long long*);

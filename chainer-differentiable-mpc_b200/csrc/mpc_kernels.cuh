@@ -212,6 +212,7 @@ struct MpcFwdParams {
   int* n_qp;                                                // [T,B]   1 + i per timestep
   unsigned char* free_mask;                                 // [T,B,m]
   int* n_ls; int* flags;                                    // [B]
+  const int* skip;                                          // device flag (nullable): non-zero -> the launch is a no-op
 };
 
 // pendulum step (env_dx/pendulum.py:65-102, `simple` model); x=(cos,sin,dth), returns x'
@@ -297,6 +298,7 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
   int e = blockIdx.x * epb + eloc;
   const bool valid = e < B;
   if (!valid) e = B - 1;
+  if (p.skip && *p.skip) return;                          // device-resident BoxDDP loop already exited (uniform)
   const MpcLayout L = mpc_layout<R>(n, m);
   R* sm = reinterpret_cast<R*>(smem_raw) + (size_t)eloc * L.stride;
   R* Q = sm + L.Q; R* q = sm + L.q; R* V = sm + L.V; R* v = sm + L.v; R* Mx = sm + L.Mx; R* mv = sm + L.mv;
@@ -526,11 +528,8 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
     } else {
       const bool worse = cost > old_cost;             // NaN -> accepted, as in the reference
       if (!worse) done = true;
-      else {
-        alpha *= p.ls_decay;
-        ++trial;
-        if (trial >= p.max_ls_trials) { status |= FLAG_LS_CAPPED; done = true; }
-      }
+      else if (trial + 1 >= p.max_ls_trials) { status |= FLAG_LS_CAPPED; ++trial; done = true; }   // alpha stays the one of the
+      else { alpha *= p.ls_decay; ++trial; }                                                        // trajectory just written
     }
   }
   if (valid && g.lane == 0) {
@@ -557,10 +556,12 @@ struct TrajParams {
   R dyn_params[5];
   R* x;            // [T,B,n]
   R* Fout; R* fout;  // pendulum linearisation outputs [T-1,B,3,4], [T-1,B,3] (nullable)
+  const int* skip;   // device flag (nullable): non-zero -> the launch is a no-op
 };
 
 template <typename R, int NMAX>
 __global__ void traj_kernel(TrajParams<R> p) {
+  if (p.skip && *p.skip) return;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.B) return;
   const int n = p.n, m = p.m, s = n + m, T = p.T;

@@ -2,7 +2,9 @@
 // Compiled once per dtype (-DDMPC_REAL=double|float) so the two builds run in parallel.
 #include "launch.h"
 #include "mpc_kernels.cuh"
+#include "mpc_tpe_kernel.cuh"
 #include "mpc_launch.h"
+#include <cstdlib>
 
 #ifndef DMPC_REAL
 #define DMPC_REAL double
@@ -37,8 +39,56 @@ static int launch_elems(K kernel, const P& p, int G, size_t stride_bytes, int B,
 
 #define MPC_SHAPES(X) X(3, 1, 4) X(4, 2, 8) X(8, 4, 16)
 
+// m = 1, n <= 3: one thread per element, everything in registers (mpc_tpe_kernel.cuh).  DMPC_MPC_GROUP=1 selects the
+// group-per-element kernel for A/B runs.
+template <int N>
+static int launch_mpc_tpe(const MpcFwdParams<Rr>& p, bool batch, cudaStream_t st, long long* nl) {
+  // four candidate lanes per element (speculative parallel line search) while the K_t, k_t hand-over fits shared memory
+  // and - for batch coupling - the whole batch still fits one 256-thread CTA; otherwise one lane per element
+  const size_t kk = (size_t)p.T * (N + 1) * sizeof(Rr);            // bytes per element
+  static int spec = -1;
+  if (spec < 0) { const char* e = getenv("DMPC_MPC_NO_SPEC"); spec = (e && e[0] == '1') ? 0 : 1; }
+  if (batch) {
+    const int t4 = ((p.B * 4 + 31) / 32) * 32, t1 = ((p.B + 31) / 32) * 32;
+    if (spec && t4 <= 256 && (t4 / 4) * kk <= (size_t)kMaxSmem) {
+      auto k = mpc_forward_tpe_kernel<Rr, N, true, 256, 4>;
+      const size_t sm = (t4 / 4) * kk;
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA;
+      k<<<1, t4, sm, st>>>(p);
+    } else if (t1 <= 256) mpc_forward_tpe_kernel<Rr, N, true, 256, 1><<<1, t1, 0, st>>>(p);
+    else if (t1 <= 1024) mpc_forward_tpe_kernel<Rr, N, true, 1024, 1><<<1, t1, 0, st>>>(p);
+    else return DMPC_ERR_UNSUPPORTED;
+  } else {
+    const int epb = 16;                                            // elements per CTA: many small CTAs spread over the SMs
+    if (spec && epb * kk <= (size_t)kMaxSmem) {
+      auto k = mpc_forward_tpe_kernel<Rr, N, false, 256, 4>;
+      const size_t sm = epb * kk;
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA;
+      k<<<(p.B + epb - 1) / epb, epb * 4, sm, st>>>(p);
+    } else {
+      const int tpb = p.B >= 148 * 128 ? 64 : 32;
+      mpc_forward_tpe_kernel<Rr, N, false, 256, 1><<<(p.B + tpb - 1) / tpb, tpb, 0, st>>>(p);
+    }
+  }
+  if (nl) ++*nl;
+  return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+}
+
+static bool mpc_tpe_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DMPC_MPC_GROUP"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 template <>
 int launch_mpc_forward<Rr>(const MpcFwdParams<Rr>& p, cudaStream_t st, long long* nl) {
+  if (p.m == 1 && mpc_tpe_enabled() && (p.dynamics == DMPC_DYN_LINEAR || p.n == 3)) {
+    const bool b = p.coupling == DMPC_COUPLING_BATCH;
+    if (!(b && p.B > 1024)) {
+      if (p.n == 3) return launch_mpc_tpe<3>(p, b, st, nl);
+      if (p.n == 2) return launch_mpc_tpe<2>(p, b, st, nl);
+    }
+  }
   const MpcLayout L = mpc_layout<Rr>(p.n, p.m);
   const size_t sb = (size_t)L.stride * sizeof(Rr);
   const bool batch = p.coupling == DMPC_COUPLING_BATCH;

@@ -95,6 +95,34 @@ class DiffLqr(FunctionNodeBase):
         u = d["u"].download(self._host_buf("u", (T, B, m)))
         return x, u
 
+    def apply_shared_numpy(self, x_init, C, c, large_f, f=None):
+        """Shared-parameter entry: C [s,s], c [s], large_f [n,s] (and f [n] or None) are ONE block each, broadcast over
+        [T, B] on the device (dmpc_expand_time_batch) instead of being repeated on the host and pushed through PCIe -
+        what LqrNet / LqrNet_cost_dx do with util.expand_time_batch (reference differentiable_lqr.py:186-198, 237-248).
+        Pair with backward_reduced_numpy, which returns the matching (T,B)-summed gradients."""
+        T, B, n, m, s, dt = self.T, self.n_batch, self.n_state, self.n_ctrl, self.n_sc, self.dtype
+        x_init = as_f(x_init, dt)
+        C, c, Fm = as_f(C, dt), as_f(c, dt), as_f(large_f, dt)
+        assert list(x_init.shape) == [B, n] and list(C.shape) == [s, s] and list(c.shape) == [s] and list(Fm.shape) == [n, s]
+        d = self._buffers()
+        ctx = self._ctx
+        blk = ctx.to_device(np.concatenate((C.ravel(), c.ravel(), Fm.ravel(), np.zeros(n, dt) if f is None else as_f(f, dt).ravel())))
+        d["x0"].upload(x_init)
+        w = dt.itemsize
+        ctx.expand_time_batch(dt, T, B, blk.ptr, d["C"], s * s)
+        ctx.expand_time_batch(dt, T, B, blk.ptr + w * s * s, d["c"], s)
+        if T > 1:
+            ctx.expand_time_batch(dt, T - 1, B, blk.ptr + w * (s * s + s), d["F"], n * s)
+            if f is not None:
+                ctx.expand_time_batch(dt, T - 1, B, blk.ptr + w * (s * s + s + n * s), d["f"], n)
+        self._have_f = f is not None
+        ctx.lqr_solve(dt, T, B, n, m, d["x0"], d["C"], d["c"], d["F"], T - 1, d["f"] if self._have_f else None,
+                      d["x"], d["u"], d["Ks"], d["ks"], d["fac"],
+                      _native.LQR_FACTOR | _native.LQR_ROLLOUT | _native.LQR_SAVE_FAC)
+        x = d["x"].download(self._host_buf("x", (T, B, n)), sync=False)
+        u = d["u"].download(self._host_buf("u", (T, B, m)))
+        return x, u
+
     def backward_numpy(self, grad_x, grad_u):
         T, B, n, m, s, dt = self.T, self.n_batch, self.n_state, self.n_ctrl, self.n_sc, self.dtype
         d = self._buffers()

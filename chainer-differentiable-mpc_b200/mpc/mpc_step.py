@@ -153,9 +153,9 @@ class MPCstep(FunctionNodeBase):
                      ("n_ls", (B,), np.int32), ("flags", (B,), np.int32)]
         packed = sum(a.nbytes for a in ins.values()) <= _native.PACK_LIMIT_BYTES
         if packed:
-            pin = _native.PackedBuffers(ctx, [(k, a.shape, dt) for k, a in ins.items()])
+            pin = _native.PackedBuffers.acquire(ctx, [(k, a.shape, dt) for k, a in ins.items()])
             d = pin.upload(ins)
-            pout = _native.PackedBuffers(ctx, out_specs)
+            pout = _native.PackedBuffers.acquire(ctx, out_specs)
             o = pout.views
         else:
             d = {k: ctx.to_device(a) for k, a in ins.items()}
@@ -172,7 +172,7 @@ class MPCstep(FunctionNodeBase):
                              o["alphas"], o["n_qp"], o["free"], o["n_ls"], o["flags"])
         if packed:
             r = pout.download()
-            pin.free(); pout.free()
+            pin.release(); pout.release()
         else:
             r = {k: v.download() for k, v in o.items()}
         flags = r["flags"]

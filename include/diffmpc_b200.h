@@ -232,6 +232,8 @@ typedef struct {
   int max_iter;
   int max_ls_trials;        /* safety cap of the per-element line search (<= 0: 64) */
   int coupling;             /* DMPC_COUPLING_* */
+  int poll_every;           /* iterations enqueued between two reads of the device-side loop record (<= 0: 8); the exit
+                               tests themselves run on the device after every iteration, so the result does not depend on it */
 } dmpc_boxddp_opts;
 
 enum { DMPC_BOXDDP_MAX_ITER = 0, DMPC_BOXDDP_CONVERGED = 1, DMPC_BOXDDP_NOT_IMPROVED = 2 };
@@ -255,6 +257,11 @@ int dmpc_boxddp_solve(dmpc_handle h, int dtype, int T, int B, int n, int m,
  *   summed in a fixed order (deterministic); d_dx0[B,n] stays per element.
  * The result feeds the NCCL all-reduce of the training step directly (a few hundred doubles per rank).
  */
+/* util.expand_time_batch on the device (reference util.py:361-377; callers differentiable_lqr.py:186-198,
+ * mpc_net.py:78-80, il_env.py:120-129): d_dst[t][b][0..count) = d_src[0..count) for t < T, b < B.  The forward half of the
+ * shared-parameter path; its backward is the fused (T,B)-sum of dmpc_*_reduced below. */
+int dmpc_expand_time_batch(dmpc_handle h, int dtype, int T, int B, int count, const void* d_src, void* d_dst, void* stream);
+
 size_t dmpc_reduced_grad_elems(int n, int m);
 int dmpc_lqr_adjoint_reduced(dmpc_handle h, int dtype, int T, int B, int n, int m,
                              const void* d_C, const void* d_c, const void* d_F, const void* d_x, const void* d_u,

@@ -79,3 +79,33 @@ def test_lqrnet_training_trace_on_gpu():
         ml = np.mean((LA - A) ** 2) + np.mean((LB - Bm) ** 2)
         if i in want:
             assert abs(loss - want[i][0]) < 1e-6 and abs(ml - want[i][1]) < 1e-6, (i, loss, ml)
+
+
+@pytest.mark.parametrize("T,B,n,m", [(9, 37, 4, 2), (12, 10, 32, 8), (1, 5, 3, 1)])
+def test_difflqr_shared_parameter_entry(T, B, n, m):
+    """DiffLqr.apply_shared_numpy: ONE C, c, A|B, f block broadcast over [T,B] on the device (dmpc_expand_time_batch =
+    util.expand_time_batch, reference util.py:361-377, as LqrNet_cost_dx.forward uses it, differentiable_lqr.py:237-248)
+    gives bit-identical x, u to the host-side broadcast, and backward_reduced_numpy the sum of the full gradients."""
+    import differentiable_lqr as dl
+    rs = np.random.RandomState(T + n)
+    s = n + m
+    L = 0.3 * rs.randn(s, s)
+    C = L @ L.T + np.eye(s) + 0.05 * rs.randn(s, s)            # not symmetric (Q10)
+    c = rs.randn(s)
+    A = np.eye(n) * 0.9 + 0.05 * rs.randn(n, n)
+    F = np.concatenate((A, rs.randn(n, m)), axis=1)
+    f = 0.1 * rs.randn(n)
+    x0 = rs.randn(B, n)
+    gx, gu = rs.randn(T, B, n), rs.randn(T, B, m)
+    bc = lambda a, t: np.ascontiguousarray(np.broadcast_to(a, (t, B) + a.shape))
+    node = dl.DiffLqr(T, B, n, m)
+    x1, u1 = node.apply_numpy(x0, bc(C, T), bc(c, T), bc(F, T - 1), bc(f, T - 1))
+    full = node.backward_numpy(gx, gu)
+    node2 = dl.DiffLqr(T, B, n, m)
+    x2, u2 = node2.apply_shared_numpy(x0, C, c, F, f)
+    assert np.array_equal(x1, x2) and np.array_equal(u1, u2)
+    dx0, sC, sc, sF, sf = node2.backward_reduced_numpy(gx, gu)
+    assert rel_err(dx0, full[0]) < 1e-12
+    assert rel_err(sC, full[1].sum(axis=(0, 1))) < 1e-12 and rel_err(sc, full[2].sum(axis=(0, 1))) < 1e-12
+    if T > 1:
+        assert rel_err(sF, full[3].sum(axis=(0, 1))) < 1e-12 and rel_err(sf, full[4].sum(axis=(0, 1))) < 1e-12
