@@ -982,14 +982,16 @@ def il_iteration(B=8192, reps=3, dist=None, dev=None, rank=0, world=1, local=0):
     from box_ddp import BoxDDP
     from util import QuadCost
     from pendulum_dx import PendulumDx
-    rs = np.random.RandomState(1000 * rank)
+    rs = np.random.RandomState(1000 * rank)        # rank 0 draws exactly the round-1 instance (seed 0)
     th = rs.rand(B) * np.pi - np.pi / 2
     x0 = np.stack((np.cos(th), np.sin(th), rs.rand(B) * 2 - 1), axis=1)
     dx = PendulumDx()
     qv, pv = dx.get_true_obj()
     T = 20
-    rp = np.random.RandomState(7)                 # the learner's parameters are shared by all ranks
-    q_learn = qv * (1.0 + 0.1 * rp.randn(4)); p_learn = pv + 0.05 * rp.randn(4)
+    rp = np.random.RandomState(0); rp.rand(B); rp.rand(B)      # the learner's parameters are shared by all ranks:
+    q_learn = qv * (1.0 + 0.1 * rp.randn(4)); p_learn = pv + 0.05 * rp.randn(4)     # rank 0's stream, replayed
+    if rank == 0:
+        rs.randn(4); rs.randn(4)
     Q = np.repeat(np.repeat(np.diag(q_learn)[None, None], T, 0), B, 1)
     p = np.repeat(np.repeat(p_learn[None, None], T, 0), B, 1)
     u_exp = np.clip(rs.randn(T, B, 1), -2, 2)

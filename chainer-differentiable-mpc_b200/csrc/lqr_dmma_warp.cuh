@@ -113,7 +113,7 @@ struct WarpCfg {
   static constexpr int LDK = 34;     // K panel [8][34]: B fragments by rows 2t+e (aliases the Qux panel)
   static constexpr int OQux = OSCR, OK = OQux, OQuu = OQux + M * LDQ, OQi = OQuu + M * LDU, Oqu = OQi + M * LDU,
                        Okk = Oqu + M, Omv = Okk + M, Obar = Omv + N;                     // two mbarriers per warp
-  static constexpr int TOTAL = Obar + 2;
+  static constexpr int Oqall = Obar + 2, TOTAL = Oqall + S;                          // q = c + F^T mv, all 40 rows
   // rollout: two stages {F, f, K_t [8][36], k_t} carved from the same region, then x|u and x_next
   static constexpr int LDKR = 36;
   static constexpr int RF = 0, Rf = RF + N * LDF, RK = Rf + N, Rk = RK + M * LDKR, RSTG = Rk + M;
@@ -240,26 +240,21 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
 
       double WT[5][4][2];          // WT[j][r][e] = W[8r+2t+e][8j+g],  W = V F
       if (!last) {
-        // ---- mv = V f + v.  V f is a DMMA product too (B operand = f in column 0, zero elsewhere): a scalar DFMA issued
-        //      while the other warp of the sub-partition streams DMMAs waits for the FP64 pipe as long as a DMMA does
-        //      (profiles/r2/fwd_pass_stalls.txt), and its shuffle reduction adds a dependent chain on top
+        // ---- mv = V f + v
         double mvr[4];
-        if (have_f) {
-          double mvt[4][2];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) { mvt[r][0] = 0.0; mvt[r][1] = 0.0; }
+        for (int r = 0; r < 4; ++r) {
+          double a = 0.0;
+          if (have_f) {
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
-            const double2 f2 = ld2<IO>(fs + kb * 8 + 2 * tg);
-            const double b0 = (gr == 0) ? f2.x : 0.0, b1 = (gr == 0) ? f2.y : 0.0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) { dmma(mvt[r], Vr[r][kb][0], b0); dmma(mvt[r], Vr[r][kb][1], b1); }
+            for (int kb = 0; kb < 4; ++kb) {
+              const double2 f2 = ld2<IO>(fs + kb * 8 + 2 * tg);
+              a = __fma_rn(Vr[r][kb][0], f2.x, a);
+              a = __fma_rn(Vr[r][kb][1], f2.y, a);
+            }
+            a = quad_sum(a);
           }
-#pragma unroll
-          for (int r = 0; r < 4; ++r) mvr[r] = mvt[r][0] + v_s[r * 8 + gr];      // lanes t = 0 hold column 0
-        } else {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) mvr[r] = v_s[r * 8 + gr];
+          mvr[r] = a + v_s[r * 8 + gr];
         }
         __syncwarp();                                  // every lane has read v before mv overwrites it
         if (tg == 0) {
@@ -287,10 +282,35 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
         __syncwarp();                                  // mv_s complete
       }
 
-      // ---- Q = C + F^T W, row block u first; q = c + F^T mv rides along as a sixth accumulator tile whose B operand is
-      //      mv in column 0 (8 extra DMMAs per pass instead of 8 DFMAs + 2 shuffles per lane that would each wait for the
-      //      FP64 pipe).  After the first pass the Gauss-Jordan inverse of Quu, K = -Quu^-1 Qux and k = -Quu^-1 qu run as
-      //      one scalar section; the four Qxx passes that follow are pure DMMA streams.
+      // ---- q = c + F^T mv for all 40 rows as ONE scalar section.  DFMAs share the FP64 pipe with the DMMAs: issued
+      //      between them (one per k-step, as round 1 did) each one waits for the DMMA in flight and costs a whole DMMA
+      //      slot (profiles/r2/fwd_pass_stalls.txt); issued back to back here they do not break up the DMMA streams of
+      //      the Q passes.  (Folding q, mv and v into extra DMMA tiles instead - 480 DMMAs per step - measured slower:
+      //      profiles/r2/forward_variants_ab.txt.)
+      double* qall_s = sm + Cfg::Oqall;
+      if (!last) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;           // rows 0..31: lane l owns row l (column l of F_t)
+#pragma unroll
+        for (int k = 0; k < N; k += 4) {
+          a0 = __fma_rn((double)Fs[(k + 0) * LDF + lane], mv_s[k + 0], a0);
+          a1 = __fma_rn((double)Fs[(k + 1) * LDF + lane], mv_s[k + 1], a1);
+          a2 = __fma_rn((double)Fs[(k + 2) * LDF + lane], mv_s[k + 2], a2);
+          a3 = __fma_rn((double)Fs[(k + 3) * LDF + lane], mv_s[k + 3], a3);
+        }
+        double b0 = 0.0;                                           // rows 32..39: row 32 + g by the four lanes of a quad
+#pragma unroll
+        for (int k = 0; k < N; k += 4) b0 = __fma_rn((double)Fs[(k + tg) * LDF + N + gr], mv_s[k + tg], b0);
+        b0 = quad_sum(b0);
+        qall_s[lane] = ((a0 + a1) + (a2 + a3)) + (double)cs[lane];
+        if (tg == 0) qall_s[N + gr] = b0 + (double)cs[N + gr];
+      } else {
+        qall_s[lane] = (double)cs[lane];
+        if (lane < M) qall_s[N + lane] = (double)cs[N + lane];
+      }
+      __syncwarp();
+
+      // ---- Q = C + F^T W, row block u first.  After that pass the Gauss-Jordan inverse of Quu, K = -Quu^-1 Qux and
+      //      k = -Quu^-1 qu run as a second scalar section; the four Qxx passes that follow are pure DMMA streams.
       double Qxx[4][4][2], Qxu[4][2];
       IO* fg = save_fac ? p.fac + idx * (M * M + N * M) : nullptr;
 #pragma unroll
@@ -344,21 +364,17 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
             st2(Kg + c * 8, k2.x, k2.y);
           }
         }
-        double acc5[2] = {0.0, 0.0};
         if (!last) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const double2 m2 = *reinterpret_cast<const double2*>(mv_s + r * 8 + 2 * tg);
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int ee = 0; ee < 2; ++ee) {
               const double a = Fs[(r * 8 + 2 * tg + ee) * LDF + i * 8 + gr];
 #pragma unroll
               for (int j = 0; j < 5; ++j) dmma(acc[j], a, WT[j][r][ee]);
-              dmma(acc5, a, (gr == 0) ? (ee ? m2.y : m2.x) : 0.0);
             }
-          }
         }
-        const double qa = acc5[0] + (double)cs[i * 8 + gr];          // lanes t = 0 hold column 0 of the sixth tile
+        const double qa = qall_s[i * 8 + gr];
         if (i == 4) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -394,18 +410,9 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
             for (int r = 0; r < 4; ++r) dmma(Qxx[r][c], Qxu[r][ee], b);
           }
         IO* Vg = p.Vsave ? p.Vsave + idx * (N * N + N) : nullptr;     // V_t | v_t for the fused adjoint (lambda = V x + v)
-        double vacc[4][2];                            // v = qx + Qxu k as a fifth column tile (B operand = k in column 0)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) { vacc[r][0] = 0.0; vacc[r][1] = 0.0; }
-#pragma unroll
-        for (int ee = 0; ee < 2; ++ee) {
-          const double b5 = (gr == 0) ? (ee ? kp.y : kp.x) : 0.0;
-#pragma unroll
-          for (int r = 0; r < 4; ++r) dmma(vacc[r], Qxu[r][ee], b5);
-        }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const double vn = qx_s[r * 8 + gr] + vacc[r][0];
+          const double vn = qx_s[r * 8 + gr] + quad_sum(__fma_rn(Qxu[r][0], kp.x, Qxu[r][1] * kp.y));
           if (tg == 0) { v_s[r * 8 + gr] = vn; if (Vg) Vg[N * N + r * 8 + gr] = (IO)vn; }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
