@@ -22,7 +22,7 @@ ADJ_STRICT_REFERENCE = 1
 ADJ_STAGE_DTAU_ONLY, ADJ_STAGE_OUT_ONLY = 2, 4
 COUPLING_ELEMENT, COUPLING_BATCH = 0, 1
 DYN_LINEAR, DYN_PENDULUM = 0, 1
-FLAG_QP_NOT_CONVERGED, FLAG_NONFINITE, FLAG_LS_CAPPED = 1, 2, 4
+FLAG_QP_NOT_CONVERGED, FLAG_NONFINITE, FLAG_LS_CAPPED, FLAG_BAD_BOUNDS = 1, 2, 4, 8
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

@@ -290,6 +290,7 @@ static int boxddp_impl(dmpc_handle h, int dtype, int T, int B, int n, int m, con
   }
   const int n_iter = hc.n_iter, status = hc.done ? hc.status : DMPC_BOXDDP_MAX_ITER, flags_or = hc.flags_or;
   if (hc.nonfinite) { if (h_n_iter) *h_n_iter = n_iter; return fail(h, DMPC_ERR_NONFINITE, "boxddp: non-finite trajectory, cost or step norm"); }
+  if (flags_or & DMPC_FLAG_BAD_BOUNDS) { if (h_n_iter) *h_n_iter = n_iter; return fail(h, DMPC_ERR_BAD_BOUNDS, "boxddp: lower is larger than upper"); }
   if (du_last) CK(cudaMemcpyAsync(du_last, du, sizeof(R) * (size_t)B, cudaMemcpyDeviceToDevice, st));
   if (pend) {   // linearise at the returned point (box_ddp.py:235-242); the rollout itself is scratch
     int rc = dmpc_get_traj(h, dtype, T, B, n, m, dynamics, x_best, u_best, nullptr, nullptr, dynp, x_nom, F_lin, f_lin, st);

@@ -19,6 +19,7 @@ enum ElemFlag : int {
   FLAG_QP_NOT_CONVERGED = DMPC_FLAG_QP_NOT_CONVERGED,
   FLAG_NONFINITE = DMPC_FLAG_NONFINITE,
   FLAG_LS_CAPPED = DMPC_FLAG_LS_CAPPED,
+  FLAG_BAD_BOUNDS = DMPC_FLAG_BAD_BOUNDS,
 };
 
 // ---------------------------------------------------------------- pinned arithmetic

@@ -172,8 +172,12 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gr = lane >> 2, tg = lane & 3;
   const int T = p.T, B = p.B;
-  const int e = blockIdx.x * WPC + warp;
-  if (e >= B) return;                       // warps never synchronise CTA-wide below this point
+  // Persistent warps: at most two CTAs per SM are launched and warp gw owns the elements gw, gw + nw, gw + 2 nw, ...
+  // (no CTA relaunch between elements, no idle warps in a partially filled last wave: -3.5 % on config 5).  Skewing the
+  // sweep / rollout order between the warps of a CTA (sweep k elements, then roll k out) was measured too and is within
+  // noise of this plain order (profiles/r2/forward_variants_ab.txt).
+  const int nw = gridDim.x * WPC, gw = blockIdx.x * WPC + warp;
+  if (gw >= B) return;                      // warps never synchronise CTA-wide below this point
   double* sm = reinterpret_cast<double*>(smem_raw) + (size_t)warp * Cfg::TOTAL;
   const size_t tb = (size_t)B;
   const bool have_f = p.f != nullptr;
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
   __syncwarp();
   unsigned par0 = 0, par1 = 0;
 
+  for (int e = gw; e < B; e += nw) {
   if (p.flags & LQR_DO_FACTOR) {
     IO* Fs = reinterpret_cast<IO*>(sm + Cfg::OF); IO* fs = reinterpret_cast<IO*>(sm + Cfg::Of);
     IO* cs = reinterpret_cast<IO*>(sm + Cfg::Oc); IO* Cs = reinterpret_cast<IO*>(sm + Cfg::OC);
@@ -490,6 +495,7 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
       st ^= 1;
     }
   }
+  }   // elements of this warp
 }
 
 }  // namespace dmpc

@@ -181,6 +181,7 @@ __global__ void pnqp_kernel(PnqpParams<R> p) {
   }
   sg.sync();
   unsigned fm = 0; int status = 0;
+  for (int o = 0; o < m; ++o) if (lo[o] > hi[o]) status |= FLAG_BAD_BOUNDS;                       // pnqp.py:64 asserts
   const int it = g_pnqp<SG, MMAX, BATCH>(sg, m, H, m, q, lo, hi, x, Hf, piv, rhs, gb, xh, p.n_iter, &fm, &status);
   if (valid) {
     for (int o = sg.lane; o < m; o += SG) {
@@ -340,6 +341,7 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
       // Taylor shift: c_hat = C tau + c (:305-316)
       for (int o = g.lane; o < s; o += G) tau[o] = (o < n) ? xn[o] : un[o - n];
       for (int o = g.lane; o < m; o += G) { lb[o] = lot[o] - un[o]; ub[o] = hit[o] - un[o]; }    // :136-138
+      for (int o = 0; o < m; ++o) if (lot[o] > hit[o]) status |= FLAG_BAD_BOUNDS;                 // the reference asserts (:139)
       g.sync();
       for (int o = g.lane; o < s; o += G) {
         R a = ct[o];

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
         tau[n] = p.u_nom[idx];
       }
       const R lb = p.lo[idx] - tau[n], ub = p.hi[idx] - tau[n];               // :136-138
+      if (lb > ub) status |= FLAG_BAD_BOUNDS;                                  // the reference asserts (:139)
       R Q[s][s], q[s];
 #pragma unroll
       for (int o = 0; o < s; ++o) {                                            // Taylor shift c_hat = C tau + c (:305-316)

@@ -40,8 +40,11 @@ enum dmpc_dtype { DMPC_F64 = 0, DMPC_F32 = 1 };
 enum dmpc_status {
   DMPC_OK = 0,
   DMPC_ERR_BAD_SHAPE = 1,   /* the reference's shape asserts (lqr_recursion.py:51-66, mpc_step.py:79-92) */
-  DMPC_ERR_BAD_BOUNDS = 2,  /* lower > upper (pnqp.py:64, mpc_step.py:139) */
-  DMPC_ERR_NONFINITE = 3,   /* NaN / inf asserts (mpc_step.py:133-135,161-162,284-285) */
+  DMPC_ERR_BAD_BOUNDS = 2,  /* lower > upper (pnqp.py:64, mpc_step.py:139): returned by dmpc_boxddp_solve (which reads its
+                               loop record anyway); the stream-ordered calls dmpc_pnqp / dmpc_mpc_step_forward do not
+                               synchronise and report it per element instead (DMPC_FLAG_BAD_BOUNDS in d_flags) */
+  DMPC_ERR_NONFINITE = 3,   /* NaN / inf asserts (mpc_step.py:133-135,161-162,284-285): returned by dmpc_boxddp_solve;
+                               per element DMPC_FLAG_NONFINITE elsewhere */
   DMPC_ERR_CUDA = 4,
   DMPC_ERR_UNSUPPORTED = 5,
   DMPC_ERR_NULL = 6,
@@ -52,7 +55,9 @@ enum dmpc_status {
 enum dmpc_elem_flag {
   DMPC_FLAG_QP_NOT_CONVERGED = 1, /* pnqp.py:192 "Did not converge" warning */
   DMPC_FLAG_NONFINITE = 2,
-  DMPC_FLAG_LS_CAPPED = 4         /* line search hit the safety cap (mpc_step.py:196 would not terminate) */
+  DMPC_FLAG_LS_CAPPED = 4,        /* line search hit the safety cap (mpc_step.py:196 would not terminate); d_alphas is
+                                     the alpha of the trajectory that was written */
+  DMPC_FLAG_BAD_BOUNDS = 8        /* lower > upper for this element at some timestep (the reference asserts) */
 };
 
 /* lqr_solve flags */
@@ -98,7 +103,10 @@ int dmpc_sync(dmpc_handle h, void* stream);
 long long dmpc_launch_count(dmpc_handle h);
 
 /* ---- LQR (replaces LqrRecursion, lqr/lqr_recursion.py:18-209) ------------------------ */
-/* elements (not bytes) of the factor cache written with DMPC_LQR_SAVE_FAC */
+/* elements (not bytes) of the factor cache written with DMPC_LQR_SAVE_FAC: Quu_t^-1 | Qxu_t per (t,b) [T,B,m*m+n*m], then
+ * the value function V_t | v_t per (t,b) [T,B,n*n+n] (written for the shapes whose adjoint runs as two sweeps on
+ * lambda_t = V_t x_t + v_t, today n=32/m=8; reserved otherwise).  Opaque to the caller: allocate, pass to lqr_solve, pass
+ * on to lqr_adjoint. */
 size_t dmpc_lqr_fac_elems(int T, int B, int n, int m);
 
 /*
@@ -107,6 +115,9 @@ size_t dmpc_lqr_fac_elems(int T, int B, int n, int m);
  *   flags = FACTOR          -> backward(): writes d_Ks[T,B,m,n], d_ks[T,B,m]
  *   flags = ROLLOUT         -> forward(Ks, ks): reads d_Ks, d_ks, writes d_x, d_u
  * d_f may be NULL (f is None).  d_fac may be NULL unless SAVE_FAC.
+ * Alignment: any alignment of the element type is accepted.  The n=32/m=8 tensor-core kernel moves C, c, F, f, Ks, ks and
+ * the factor cache with 16-byte asynchronous copies; when one of those pointers is not 16-byte aligned the call is served
+ * by the generic kernel instead (same results, slower) - cudaMalloc'ed buffers and torch tensors are always aligned.
  */
 int dmpc_lqr_solve(dmpc_handle h, int dtype, int T, int B, int n, int m,
                    const void* d_x0, const void* d_C, const void* d_c,
@@ -155,7 +166,8 @@ int dmpc_pnqp(dmpc_handle h, int dtype, int B, int m,
  *   bounds:     d_lower, d_upper [T,B,m]   (scalar bounds are broadcast by the caller, box_ddp.py:68-90)
  *   true cost:  QuadCost d_tC[T,B,s,s], d_tc[T,B,s]  (may alias d_C, d_c)
  *   true dyn:   DMPC_DYN_LINEAR with d_tF[>=T-1,B,n,s], d_tf (nullable)  or
- *               DMPC_DYN_PENDULUM with h_dyn_params = {g, m, l} (env_dx/pendulum.py:31-102)
+ *               DMPC_DYN_PENDULUM with h_dyn_params = {g, m, l, dt, max_torque} (env_dx/pendulum.py:31-102; dt and
+ *               max_torque <= 0 mean the reference's 0.05 and 2.0); five doubles are read
  * Outputs: d_x[T,B,n] d_u[T,B,m]; gains d_Ks[T,B,m,n] d_ks[T,B,m]; d_u_first[T,B,m] = controls of the
  * alpha=1 pass (for full_du_norm, :260-263); d_objs[T,B]; d_costs[B]; d_old_costs[B] (nullable);
  * d_alphas[B]; d_n_qp[T,B] int32 (1 + PNQP iterations); d_free[T,B,m] uint8; d_n_ls[B] int32

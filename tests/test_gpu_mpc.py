@@ -229,3 +229,38 @@ def test_get_traj_linear_and_pendulum(ctx):
     assert rel_err(x.download()[1], g["xn"] if False else want[1]) < 1e-13
     assert rel_err(x.download(), want) < 1e-12
     assert rel_err(Fo.download(), wF) < 1e-12 and rel_err(fo.download(), wf) < 1e-11
+
+
+def test_bad_bounds_are_reported_through_the_c_abi(ctx):
+    """lower > upper: the reference asserts (pnqp.py:64, mpc_step.py:139).  The stream-ordered C-ABI calls flag the
+    element (DMPC_FLAG_BAD_BOUNDS in d_flags); dmpc_boxddp_solve, which reads its loop record anyway, returns
+    DMPC_ERR_BAD_BOUNDS (surfaced as AssertionError by the ctypes layer, like the reference)."""
+    rs = np.random.RandomState(3)
+    B, m = 9, 3
+    L = rs.randn(B, m, m)
+    H = L @ L.transpose(0, 2, 1) + np.eye(m)
+    q = rs.randn(B, m); lo = -np.ones((B, m)); hi = np.ones((B, m))
+    lo[4, 1], hi[4, 1] = 0.5, -0.5
+    *_, fl = run_pnqp(ctx, H, q, lo, hi)
+    assert (fl[4] & _native.FLAG_BAD_BOUNDS) and not (np.delete(fl, 4) & _native.FLAG_BAD_BOUNDS).any()
+    # MPC step (group kernel, n=4 m=2) and the thread-per-element kernel (n=3 m=1)
+    for n, m in ((4, 2), (3, 1)):
+        T, B = 6, 10
+        s = n + m
+        C, c = psd_cost(rs, T, B, s)
+        F = stable_dynamics(rs, T, B, n, m, per_t=False)
+        u = np.zeros((T, B, m)); x0 = rs.randn(B, n)
+        lo = np.full((T, B, m), -0.5); hi = np.full((T, B, m), 0.5)
+        lo[2, 7, 0], hi[2, 7, 0] = 0.3, -0.3
+        g = dict(C=C, c=c, F=F, f=None, x_nom=ompc.get_traj(x0, u, ("linear", F, None)), u_nom=u, lower=lo, upper=hi, n=n, m=m)
+        g.pop("f")
+        r, d = run_mpc_forward(ctx, g, _native.COUPLING_ELEMENT)
+        assert r["flags"][7] & _native.FLAG_BAD_BOUNDS and not (np.delete(r["flags"], 7) & _native.FLAG_BAD_BOUNDS).any()
+    # BoxDDP: status code
+    T, B, n, m = 6, 10, 3, 1
+    dlo, dhi = ctx.to_device(lo), ctx.to_device(hi)
+    o = [ctx.empty((T, B, n)), ctx.empty((T, B, m)), ctx.empty((B,)), ctx.empty((B,)), ctx.empty((B,))]
+    with pytest.raises(AssertionError):
+        ctx.boxddp_solve(np.float64, T, B, n, m, ctx.to_device(x0), ctx.to_device(C), ctx.to_device(c), dlo, dhi,
+                         _native.DYN_LINEAR, ctx.to_device(F), T - 1, None, None, ctx.zeros((T, B, m)), 1e-6, 1e-4, 0.2, 5, 5, 64,
+                         _native.COUPLING_ELEMENT, *o)

@@ -36,6 +36,9 @@ class _FakeCtx:
     def _release(self, ptr, nbytes):
         pass
 
+    def pinned_empty(self, shape, dtype=np.float64):      # the real context hands out page-locked memory
+        return np.empty(shape, dtype)
+
 
 def test_packed_buffers_layout_is_aligned_and_disjoint():
     import _native
@@ -52,6 +55,14 @@ def test_packed_buffers_layout_is_aligned_and_disjoint():
     spans.sort()
     assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
     assert spans[-1][1] <= pb.total
+    # acquire / release keep one instance per layout in the context
+    ctx = _FakeCtx()
+    a = _native.PackedBuffers.acquire(ctx, specs)
+    a.release()
+    b = _native.PackedBuffers.acquire(ctx, specs)
+    assert b is a
+    c = _native.PackedBuffers.acquire(ctx, specs)          # a second live user gets its own buffers
+    assert c is not a
 
 
 def test_link_lock_is_per_device_and_direction_and_serialises_bursts():
