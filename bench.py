@@ -199,6 +199,25 @@ def cpu_sharded_all_cores(n, m, T, Bc):
             "how": "%d concurrent processes, each running the oracle port on %d elements" % (P, Bc)}
 
 
+def reference_under_stub_record(n, m, T):
+    """The unmodified reference under the Chainer stub cannot run on the GPU box (/root/reference is absent there); it was
+    timed beside the oracle port in the build container (profiles/tools/time_reference_under_stub.py).  Returned as a
+    RECORDED annotation of the live port number: port / reference on the same host and inputs."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2", "reference_under_stub.json")) as fh:
+            rec = json.load(fh)
+        for cse in rec["cases"]:
+            if (cse["n"], cse["m"], cse["T"]) == (n, m, T):
+                return {"kind": "reference-under-stub (recorded in the build container, not live)",
+                        "solves_per_sec_there": cse["solves_per_sec"]["reference_under_stub"],
+                        "oracle_port_solves_per_sec_there": cse["solves_per_sec"]["oracle_port"],
+                        "port_over_reference": cse["port_over_reference"], "B_cpu": cse["B_cpu"], "host": rec["host"],
+                        "tool": "profiles/tools/time_reference_under_stub.py"}
+    except Exception:
+        pass
+    return None
+
+
 def cpu_sample_batch(n, m, T):
     # sized so one fwd+bwd takes a few seconds on ~8 host cores (BASELINE.md §2)
     return {(32, 8): 128, (8, 4): 1024, (4, 2): 4096, (3, 1): 4096}.get((n, m), 256)
@@ -269,7 +288,8 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "desc": desc, "n_state": n, "n_ctrl": m, "T": T, "batch_per_step": Bc},
             "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample,
-                             "sharded_all_cores": sharded},
+                             "all_cores_value": sharded.get("value"), "all_cores": sharded.get("cores"),
+                             "sharded_all_cores": sharded, "reference_under_stub": reference_under_stub_record(n, m, T)},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -646,9 +666,12 @@ def run_b200(args):
             Bcpu = cpu_sample_batch(n, m, T)
             cpu_lqr_fwd_bwd(n, m, T, min(Bcpu, 32))
             tcpu = min(cpu_lqr_fwd_bwd(n, m, T, Bcpu) for _ in range(2))
+            sharded = cpu_sharded_all_cores(n, m, T, max(Bcpu // 2, 8))
             line["cpu_baseline"] = {"value": Bcpu / tcpu, "unit": "solves/s", "cores": cpu_threads_used(), "kind": "port",
                                     "host_cpus": os.cpu_count(),
-                                    "sharded_all_cores": cpu_sharded_all_cores(n, m, T, max(Bcpu // 2, 8)),
+                                    "all_cores_value": sharded.get("value"), "all_cores": sharded.get("cores"),
+                                    "sharded_all_cores": sharded,
+                                    "reference_under_stub": reference_under_stub_record(n, m, T),
                                     "sample": "oracle port of DiffLqr.apply+backward (numpy, BLAS threads at their default), "
                                               "B_cpu=%d, same n/m/T, best of 2" % Bcpu}
         if world == 1 and not args.no_latency:
