@@ -56,6 +56,39 @@ struct Grp {
   __device__ __forceinline__ int shift() const { return (G <= 32) ? ((threadIdx.x & 31) & ~(G - 1)) : 0; }
 };
 
+// ---------------------------------------------------------------- batch-wide OR (coupling = BATCH)
+// The reference's PNQP decides on xp.sum / xp.max over the WHOLE batch (pnqp.py:139-144, 172-187).  One CTA:
+// __syncthreads_or.  Batch spread over the CTAs of a thread-block cluster (up to 16): every CTA publishes its OR in its own
+// shared memory, a cluster barrier, then everybody reads all ranks' flags through distributed shared memory.  Two flag slots
+// used alternately: a slot is rewritten two decisions later, i.e. after a cluster barrier that every reader of its old value
+// has passed.  `phase` is per-thread state (identical in all threads of the cluster).
+__device__ __forceinline__ unsigned cluster_nctas() { unsigned n; asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(n)); return n; }
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ int batch_or(int pred, unsigned& phase) {
+  int v = __syncthreads_or(pred);
+  const unsigned nr = cluster_nctas();
+  if (nr > 1) {
+    __shared__ int batch_flag[2];
+    if (threadIdx.x == 0) batch_flag[phase] = v;
+    cluster_barrier();
+    const unsigned local = (unsigned)__cvta_generic_to_shared(&batch_flag[phase]);
+    int r = 0;
+    for (unsigned k = 0; k < nr; ++k) {
+      unsigned remote; int f;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(k));
+      asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(f) : "r"(remote) : "memory");
+      r |= f;
+    }
+    phase ^= 1u;
+    v = r;
+  }
+  return v;
+}
+// before a CTA of a cluster exits: nobody may still be reading its flags
+__device__ __forceinline__ void batch_or_finish() { if (cluster_nctas() > 1) cluster_barrier(); }
+
 // ---------------------------------------------------------------- cp.async
 __device__ __forceinline__ void cp_async16(void* s, const void* g) {
   unsigned a = (unsigned)__cvta_generic_to_shared(s);

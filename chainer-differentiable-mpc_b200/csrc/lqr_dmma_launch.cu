@@ -1,6 +1,7 @@
 // Launch of the n=32, m=8 Riccati sweep on the FP64 tensor cores (lqr_dmma_warp.cuh): its own translation unit so that
 // the 255-register kernel compiles in parallel with the generic kernels.  Compiled once per dtype (-DDMPC_REAL).
 // R = float: the same kernel with float tensors in HBM and in the staging buffers, fp64 arithmetic.
+#include <cstdlib>
 #include "launch.h"
 #include "lqr_dmma_warp.cuh"
 

@@ -191,6 +191,10 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
   unsigned par0 = 0, par1 = 0;
 
   for (int e = gw; e < B; e += nw) {
+  // The staging region is re-used from the rollout of the previous element (generic-proxy reads and writes) by the bulk
+  // copies of this sweep (async proxy): order them once per element.
+  __syncwarp();
+  fence_proxy_async();
   if (p.flags & LQR_DO_FACTOR) {
     IO* Fs = reinterpret_cast<IO*>(sm + Cfg::OF); IO* fs = reinterpret_cast<IO*>(sm + Cfg::Of);
     IO* cs = reinterpret_cast<IO*>(sm + Cfg::Oc); IO* Cs = reinterpret_cast<IO*>(sm + Cfg::OC);
@@ -327,15 +331,6 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
           const double2 c2 = ld2<IO>(Cs + (i * 8 + gr) * S + j * 8 + 2 * tg);
           acc[j][0] = c2.x; acc[j][1] = c2.y;
         }
-        __syncwarp();
-        // Generic-proxy reads of this row block (the loads above, already consumed into registers) are ordered before
-        // the async-proxy refill by the warp barrier - the same read-then-release pattern as a TMA pipeline's consumer
-        // release; a fence.proxy.async here costs ~6 % of the kernel (it drains every outstanding memory operation)
-        // and is only required in the other direction (generic writes later read by the async proxy).
-        if (t > 0 && lane == 0) {                      // refill this row block for the next step
-          if (pi == 0) mbar_arrive_expect_tx(barC, S * S * W);
-          stage_C_rows(t - 1, i);
-        }
         if (pi == 1) {
           double cinv[M];
 #pragma unroll
@@ -378,6 +373,19 @@ __global__ void __launch_bounds__(WPC * 32, 8 / WPC) lqr_factor_dmma_warp_kernel
 #pragma unroll
               for (int j = 0; j < 5; ++j) dmma(acc[j], a, WT[j][r][ee]);
             }
+        }
+        // Refill this row block of the C buffer for the next step (async proxy, bulk copy).  It is issued BEHIND the DMMAs
+        // of the pass: they read every lane's accumulator registers, so every lane's loads of the row block above have
+        // completed when the copy is issued.  Round 1 issued it right after the loads with only a warp barrier in between
+        // (loads are ISSUED then, not complete): once every ~1e6 element-steps the refill overtook a load and one element's
+        // recursion went wrong (scratch/stress_c5.py, profiles/r2/forward_race.txt).  The last horizon step has no DMMAs:
+        // there the loads are ordered by an explicit proxy fence (once per element).
+        if (t > 0) {
+          if (last) { fence_proxy_async(); __syncwarp(); }
+          if (lane == 0) {
+            if (pi == 0) mbar_arrive_expect_tx(barC, S * S * W);
+            stage_C_rows(t - 1, i);
+          }
         }
         const double qa = qall_s[i * 8 + gr];
         if (i == 4) {

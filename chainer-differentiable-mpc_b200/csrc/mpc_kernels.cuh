@@ -57,7 +57,7 @@ __device__ __forceinline__ R qp_objective(const R* H, int ldh, const R* q, const
 template <int SG, int MMAX, bool BATCH, typename R>
 __device__ __forceinline__ int g_pnqp(const Grp<SG>& sg, int m, const R* H, int ldh, const R* q, const R* lo,
                                       const R* hi, R* x, R* Hf, int* piv, R* rhs, R* gbuf, R* xh,
-                                      int n_iter, unsigned* free_mask, int* status) {
+                                      int n_iter, unsigned* free_mask, int* status, unsigned& bphase) {
   const int r = sg.lane;
   unsigned act = 0;
   int it = 0;
@@ -89,7 +89,7 @@ __device__ __forceinline__ int g_pnqp(const Grp<SG>& sg, int m, const R* H, int 
     for (int j = 0; j < m; ++j) n2 += rhs[j] * rhs[j];
     bool large = sqrt(n2) >= R(DMPC_PNQP_TOL);      // pnqp.py:139-140
     bool any_large = large;
-    if (BATCH) any_large = __syncthreads_or(large ? 1 : 0) != 0;
+    if (BATCH) any_large = batch_or(large ? 1 : 0, bphase) != 0;
     if (!any_large) break;                          // returns x *before* applying dx (Q4)
     // Armijo backtracking (pnqp.py:162-190)
     R alpha = R(1);
@@ -115,7 +115,7 @@ __device__ __forceinline__ int g_pnqp(const Grp<SG>& sg, int m, const R* H, int 
       if (fail) alpha *= R(DMPC_PNQP_DECAY);
       ++count;
       bool stop = !fail;                            // max_lhs > GAMMA or NaN
-      if (BATCH) stop = __syncthreads_or(stop ? 1 : 0) != 0;
+      if (BATCH) stop = batch_or(stop ? 1 : 0, bphase) != 0;
       go = !stop && count < DMPC_PNQP_MAX_LS;
       sg.sync();
     }
@@ -181,8 +181,10 @@ __global__ void pnqp_kernel(PnqpParams<R> p) {
   }
   sg.sync();
   unsigned fm = 0; int status = 0;
+  unsigned bphase = 0;
   for (int o = 0; o < m; ++o) if (lo[o] > hi[o]) status |= FLAG_BAD_BOUNDS;                       // pnqp.py:64 asserts
-  const int it = g_pnqp<SG, MMAX, BATCH>(sg, m, H, m, q, lo, hi, x, Hf, piv, rhs, gb, xh, p.n_iter, &fm, &status);
+  const int it = g_pnqp<SG, MMAX, BATCH>(sg, m, H, m, q, lo, hi, x, Hf, piv, rhs, gb, xh, p.n_iter, &fm, &status, bphase);
+  if (BATCH) batch_or_finish();
   if (valid) {
     for (int o = sg.lane; o < m; o += SG) {
       p.x[(size_t)e * m + o] = x[o];
@@ -312,6 +314,7 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
   const bool expand = p.need_expand != 0;
   const bool have_f = (p.f != nullptr) && !expand;       // f_hat = None after the Taylor shift (:317)
   int status = 0;
+  unsigned bphase = 0;                                   // batch_or flag slot (BATCH coupling over a cluster)
 
   // =========================== backward_rec (mpc_step.py:70-173) ===========================
   {
@@ -389,7 +392,7 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
           sg.sync();
         }
         if (worker)
-          it = g_pnqp<SG, MMAX, BATCH>(sg, m, Huu, s, quu, lb, ub, kprev, Hf, piv, rhs1, gb, xh, p.n_qp_iter, &fm, &status);
+          it = g_pnqp<SG, MMAX, BATCH>(sg, m, Huu, s, quu, lb, ub, kprev, Hf, piv, rhs1, gb, xh, p.n_qp_iter, &fm, &status, bphase);
         if (worker) {
           // K = -(LU)^-1 Qux with the rows of clamped controls zeroed (:147-157)
           for (int o = sg.lane; o < m * n; o += SG) {
@@ -439,6 +442,8 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
       st ^= 1;
     }
   }
+
+  if (BATCH) batch_or_finish();      // last batch-wide decision is behind us: other CTAs of the cluster may exit
 
   // =========================== forward_rec (mpc_step.py:175-286) ===========================
   // pass -1 evaluates the cost of the nominal trajectory (xpget_cost, :191); passes >= 0 are the

@@ -5,6 +5,8 @@
 #include "mpc_tpe_kernel.cuh"
 #include "mpc_launch.h"
 #include <cstdlib>
+#include <cstring>
+#include <cstdio>
 
 #ifndef DMPC_REAL
 #define DMPC_REAL double
@@ -14,27 +16,76 @@ namespace dmpc {
 
 typedef DMPC_REAL Rr;
 
+// Launch `grid` CTAs as ONE thread-block cluster (batch coupling across CTAs: common.cuh batch_or).  Clusters of more than
+// 8 CTAs are "non-portable" sizes the kernel has to opt in to; 16 is the hardware maximum on sm_100.
+template <typename K, typename P>
+static int launch_cluster(K kernel, const P& p, int grid, int tpb, size_t smem, cudaStream_t st) {
+  if (grid > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return DMPC_ERR_CUDA;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)tpb); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)grid; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  P pc = p;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, pc);
+  if (e != cudaSuccess) fprintf(stderr, "diffmpc: cluster launch (%d CTAs x %d threads, %zu B smem) failed: %s\n", grid, tpb, smem, cudaGetErrorString(e));
+  return e == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+}
+
+static int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fprintf(stderr, "diffmpc: %s launch failed: %s\n", what, cudaGetErrorString(e));
+  return e == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+}
+
+constexpr int kMaxClusterCtas = 16;
+constexpr size_t kMpcMaxSmem = (size_t)kMaxSmem - 256;   // dynamic shared memory: the kernels also hold a few static words (batch_or flags)
+
 template <typename K, typename P>
 static int launch_elems(K kernel, const P& p, int G, size_t stride_bytes, int B, bool one_cta, cudaStream_t st,
                         long long* nl) {
-  int tpb, epb;
-  if (G > 32) { tpb = G; epb = 1; }
+  int tpb, epb, grid;
+  bool cluster = false;
+  if (G > 32) { tpb = G; epb = 1; grid = B; }
   else if (one_cta) {
-    tpb = ((B * G + 31) / 32) * 32;
-    if (tpb > 1024) return DMPC_ERR_UNSUPPORTED;   // batch coupling needs the whole batch in one CTA
+    // batch coupling: the whole batch in one CTA, or spread evenly over the CTAs of one thread-block cluster
+    cudaFuncAttributes fa;                          // the CTA size is capped by the kernel's register count too
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return DMPC_ERR_CUDA;
+    int max_threads = fa.maxThreadsPerBlock;
+    const int regs = ((fa.numRegs + 7) / 8) * 8;
+    if (regs > 0 && 65536 / regs < max_threads) max_threads = 65536 / regs;
+    max_threads = (max_threads / 32) * 32;
+    if (max_threads > 1024) max_threads = 1024;
+    int epb_max = max_threads / G;
+    if ((size_t)epb_max * stride_bytes > kMpcMaxSmem) epb_max = (int)(kMpcMaxSmem / stride_bytes);
+    if (epb_max < 1) return DMPC_ERR_UNSUPPORTED;
+    grid = (B + epb_max - 1) / epb_max;
+    if (grid > kMaxClusterCtas) return DMPC_ERR_UNSUPPORTED;    // batch coupling needs the batch resident in one cluster
+    epb = (B + grid - 1) / grid;
+    tpb = ((epb * G + 31) / 32) * 32;
     epb = tpb / G;                                 // padded groups replicate element B-1 in their own region
+    if ((size_t)epb * stride_bytes > kMpcMaxSmem || tpb > max_threads) {
+      epb = (epb_max * G / 32) * 32 / G;           // largest warp-multiple CTA within the limits
+      if (epb < 1) return DMPC_ERR_UNSUPPORTED;
+      tpb = ((epb * G + 31) / 32) * 32; grid = (B + epb - 1) / epb;
+    }
+    if (tpb > max_threads || grid > kMaxClusterCtas) return DMPC_ERR_UNSUPPORTED;
+    cluster = grid > 1;
   } else {
     tpb = 128; epb = tpb / G;
-    while ((size_t)epb * stride_bytes > (size_t)kMaxSmem && tpb > 32) { tpb /= 2; epb = tpb / G; }
+    while ((size_t)epb * stride_bytes > kMpcMaxSmem && tpb > 32) { tpb /= 2; epb = tpb / G; }
     while (tpb > 32 && (B + epb - 1) / epb < 148 * 2) { tpb /= 2; epb = tpb / G; }
+    grid = (B + epb - 1) / epb;
   }
   const size_t smem = (size_t)epb * stride_bytes;
-  if (smem > (size_t)kMaxSmem) return DMPC_ERR_UNSUPPORTED;
+  if (smem > kMpcMaxSmem) return DMPC_ERR_UNSUPPORTED;
   if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DMPC_ERR_CUDA;
-  const int grid = one_cta ? 1 : (B + epb - 1) / epb;
-  kernel<<<grid, tpb, smem, st>>>(p);
   if (nl) ++*nl;
-  return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+  if (cluster) return launch_cluster(kernel, p, grid, tpb, smem, st);
+  kernel<<<grid, tpb, smem, st>>>(p);
+  return check_launch("element-group kernel");
 }
 
 #define MPC_SHAPES(X) X(3, 1, 4) X(4, 2, 8) X(8, 4, 16)
@@ -56,8 +107,14 @@ static int launch_mpc_tpe(const MpcFwdParams<Rr>& p, bool batch, cudaStream_t st
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA;
       k<<<1, t4, sm, st>>>(p);
     } else if (t1 <= 256) mpc_forward_tpe_kernel<Rr, N, true, 256, 1><<<1, t1, 0, st>>>(p);
-    else if (t1 <= 1024) mpc_forward_tpe_kernel<Rr, N, true, 1024, 1><<<1, t1, 0, st>>>(p);
-    else return DMPC_ERR_UNSUPPORTED;
+    else {
+      // the batch spread over the CTAs of one thread-block cluster, 256 threads (255 registers) per CTA
+      const int grid = (p.B + 255) / 256;
+      if (grid > kMaxClusterCtas) return DMPC_ERR_UNSUPPORTED;   // batch coupling: at most 16 x 256 elements
+      const int tpb = ((((p.B + grid - 1) / grid) + 31) / 32) * 32;
+      if (nl) ++*nl;
+      return launch_cluster(mpc_forward_tpe_kernel<Rr, N, true, 256, 1>, p, grid, tpb, 0, st);
+    }
   } else {
     const int epb = 16;                                            // elements per CTA: many small CTAs spread over the SMs
     if (spec && epb * kk <= (size_t)kMaxSmem) {
@@ -71,7 +128,7 @@ static int launch_mpc_tpe(const MpcFwdParams<Rr>& p, bool batch, cudaStream_t st
     }
   }
   if (nl) ++*nl;
-  return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
+  return check_launch("mpc_forward_tpe_kernel");
 }
 
 static bool mpc_tpe_enabled() {
@@ -84,7 +141,7 @@ template <>
 int launch_mpc_forward<Rr>(const MpcFwdParams<Rr>& p, cudaStream_t st, long long* nl) {
   if (p.m == 1 && mpc_tpe_enabled() && (p.dynamics == DMPC_DYN_LINEAR || p.n == 3)) {
     const bool b = p.coupling == DMPC_COUPLING_BATCH;
-    if (!(b && p.B > 1024)) {
+    if (!(b && p.B > kMaxClusterCtas * 256)) {
       if (p.n == 3) return launch_mpc_tpe<3>(p, b, st, nl);
       if (p.n == 2) return launch_mpc_tpe<2>(p, b, st, nl);
     }

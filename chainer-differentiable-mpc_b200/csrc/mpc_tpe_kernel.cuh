@@ -8,8 +8,8 @@
 // memory and no LU - PNQP for m = 1 is the scalar branch of the reference (mpc/pnqp.py:77-78, 133-134).
 //
 // Same semantics as mpc_forward_kernel (reference mpc/mpc_step.py:70-328), including both couplings: with BATCH the CTA
-// holds the whole batch (one thread per element, up to 1024) and PNQP's convergence test / line-search exit are
-// __syncthreads_or reductions, exactly where the reference has xp.sum / xp.max over the batch (pnqp.py:139-144, 172-187).
+// (or the CTAs of one thread-block cluster) hold the whole batch and PNQP's convergence test / line-search exit are
+// batch_or reductions (common.cuh), exactly where the reference has xp.sum / xp.max over the batch (pnqp.py:139-144, 172-187).
 #pragma once
 #include "mpc_kernels.cuh"
 
@@ -18,7 +18,8 @@ namespace dmpc {
 // scalar projected-Newton box QP: minimise 0.5 H x^2 + q x on [lo, hi]; x in = clamped start, out = solution.
 // Returns the iteration index like g_pnqp; *Hf_out = last masked Hessian + REG (the "factor"), *is_free = control is free.
 template <bool BATCH, typename R>
-__device__ __forceinline__ int pnqp_scalar(R H, R q, R lo, R hi, R& x, R* Hf_out, bool* is_free, int n_iter, int* status) {
+__device__ __forceinline__ int pnqp_scalar(R H, R q, R lo, R hi, R& x, R* Hf_out, bool* is_free, int n_iter, int* status,
+                                           unsigned& bphase) {
   bool act = false;
   R Hf = H;
   int it = 0;
@@ -29,7 +30,7 @@ __device__ __forceinline__ int pnqp_scalar(R H, R q, R lo, R hi, R& x, R* Hf_out
     const R dx = (act ? R(0) : -g) / Hf;
     const bool large = sqrt(dx * dx) >= R(DMPC_PNQP_TOL);                     // pnqp.py:139-140
     bool any_large = large;
-    if (BATCH) any_large = __syncthreads_or(large ? 1 : 0) != 0;
+    if (BATCH) any_large = batch_or(large ? 1 : 0, bphase) != 0;
     if (!any_large) break;                                                    // x is returned before dx is applied (Q4)
     R alpha = R(1);
     const R f0 = R(0.5) * ((x * H) * x) + q * x;
@@ -45,7 +46,7 @@ __device__ __forceinline__ int pnqp_scalar(R H, R q, R lo, R hi, R& x, R* Hf_out
       if (fail) alpha *= R(DMPC_PNQP_DECAY);
       ++count;
       bool stop = !fail;
-      if (BATCH) stop = __syncthreads_or(stop ? 1 : 0) != 0;
+      if (BATCH) stop = batch_or(stop ? 1 : 0, bphase) != 0;
       go = !stop && count < DMPC_PNQP_MAX_LS;
     }
     x = xh;
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
   const bool expand = p.need_expand != 0;
   const bool have_f = (p.f != nullptr) && !expand;          // f_hat = None after the Taylor shift (mpc_step.py:317)
   int status = 0;
+  unsigned bphase = 0;                                      // batch_or flag slot (BATCH coupling over a cluster)
   // NA > 1: K_t, k_t of the element are handed from the sweep to its candidate lanes through shared memory
   R* Kk = reinterpret_cast<R*>(smem_raw) + (size_t)(threadIdx.x / NA) * T * (n + 1);
 
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
       if (t == T - 1) kprev = fmin(fmax(-quu / Huu, lb), ub);
       else kprev = fmin(fmax(kprev, lb), ub);
       R Hf; bool is_free;
-      const int it = pnqp_scalar<BATCH>(Huu, quu, lb, ub, kprev, &Hf, &is_free, p.n_qp_iter, &status);
+      const int it = pnqp_scalar<BATCH>(Huu, quu, lb, ub, kprev, &Hf, &is_free, p.n_qp_iter, &status, bphase);
       R K[n], P[s];
 #pragma unroll
       for (int j = 0; j < n; ++j) K[j] = (is_free ? -Q[n][j] : R(0)) / Hf;    // rows of clamped controls zeroed (:147-157)
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
       }
     }
   }
+  if (BATCH) batch_or_finish();                             // the last batch-wide decision is behind us
   if (NA > 1) __syncwarp();                                 // K_t, k_t of lane a = 0 are visible to its candidate lanes
   else if (!valid) return;                                  // padding threads were only needed for the PNQP barriers
 

@@ -67,10 +67,19 @@ def _group_size(n, m):
 
 
 def resolve_coupling(coupling, B, n, m):
+    """'auto' = the reference's literal whole-batch control flow whenever the batch can be resident at once - in one CTA
+    or spread over the (up to 16) CTAs of one thread-block cluster (csrc/mpc_launch.cu launch_elems / launch_mpc_tpe) -
+    and the per-element control flow (== reference with n_batch 1) beyond that."""
     coupling = coupling or DEFAULT_COUPLING
     if coupling == "auto":
+        if m == 1 and n in (2, 3):                       # thread-per-element kernel: 256 elements per CTA
+            return "batch" if B <= 16 * 256 else "element"
         G = _group_size(n, m)
-        return "batch" if (G <= 32 and B * G <= 1024 and B * (n + m) ** 2 * 8 * 6 < 200 * 1024) else "element"
+        if G > 32:
+            return "element"
+        per_elem = (n + m) ** 2 * 8 * 6                  # shared-memory bytes per element, roughly (mpc_layout)
+        epb = max(1, min(1024 // G, (200 * 1024) // per_elem))
+        return "batch" if B <= 16 * epb else "element"
     return coupling
 
 
@@ -164,12 +173,22 @@ class MPCstep(FunctionNodeBase):
         dtF = d.get("tF", d["F"]) if dyn == _native.DYN_LINEAR else None
         dtf = d.get("tf") if dyn == _native.DYN_LINEAR else None
         coupling = resolve_coupling(self.coupling, B, n, m)
-        ctx.mpc_step_forward(dt, T, B, n, m, d["C"], d["c"], d["F"], F_hat.shape[0], d.get("f"), d["x_nom"], d["u_nom"],
-                             d["lo"], d["hi"], dtC, dtc, dyn, dtF, dtf, params, self.ls_decay,
-                             MAX_LS_TRIALS, self.need_expand,
-                             _native.COUPLING_BATCH if coupling == "batch" else _native.COUPLING_ELEMENT,
-                             o["x"], o["u"], o["Ks"], o["ks"], o["u_first"], o["objs"], o["costs"], o["old"],
-                             o["alphas"], o["n_qp"], o["free"], o["n_ls"], o["flags"])
+
+        def launch(cpl):
+            ctx.mpc_step_forward(dt, T, B, n, m, d["C"], d["c"], d["F"], F_hat.shape[0], d.get("f"), d["x_nom"], d["u_nom"],
+                                 d["lo"], d["hi"], dtC, dtc, dyn, dtF, dtf, params, self.ls_decay,
+                                 MAX_LS_TRIALS, self.need_expand,
+                                 _native.COUPLING_BATCH if cpl == "batch" else _native.COUPLING_ELEMENT,
+                                 o["x"], o["u"], o["Ks"], o["ks"], o["u_first"], o["objs"], o["costs"], o["old"],
+                                 o["alphas"], o["n_qp"], o["free"], o["n_ls"], o["flags"])
+        try:
+            launch(coupling)
+        except _native.DiffMpcError as ex:
+            # 'auto' guessed that the batch is resident at once (one CTA / one cluster); the launcher knows better
+            if not ((self.coupling or DEFAULT_COUPLING) == "auto" and coupling == "batch" and "unsupported" in str(ex)):
+                raise
+            coupling = "element"
+            launch(coupling)
         if packed:
             r = pout.download()
             pin.release(); pout.release()

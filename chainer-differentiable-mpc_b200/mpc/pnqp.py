@@ -31,8 +31,9 @@ DEFAULT_COUPLING = "auto"
 
 
 def _fits_one_cta(B, m):
+    """Whole-batch coupling needs the batch resident in one CTA or in the (up to 16) CTAs of one thread-block cluster."""
     sg = 4 if m <= 4 else (8 if m <= 8 else (16 if m <= 16 else 32))
-    return B * sg <= 1024
+    return B * sg <= 16 * 1024
 
 
 def PNQP(H, q, lower, upper, x_init=None, n_iter=20, coupling=None, device=0):
@@ -46,7 +47,8 @@ def PNQP(H, q, lower, upper, x_init=None, n_iter=20, coupling=None, device=0):
     assert list(lower.shape) == [B, d], "lower dim mismatch actual" + str(lower.shape)
     assert list(upper.shape) == [B, d], "upper dim mismatch"
     coupling = coupling or DEFAULT_COUPLING
-    if coupling == "auto":
+    auto = coupling == "auto"
+    if auto:
         coupling = "batch" if _fits_one_cta(B, d) else "element"
     ctx = _native.default_context(device)
     dev = [ctx.to_device(a) for a in (H, q, lower, upper)]
@@ -55,8 +57,14 @@ def PNQP(H, q, lower, upper, x_init=None, n_iter=20, coupling=None, device=0):
         dxi = ctx.to_device(as_f(x_init, dt))
     x = ctx.empty((B, d), dt); LU = ctx.empty((B, d, d), dt); piv = ctx.empty((B, d), np.int32)
     free = ctx.empty((B, d), dt); it = ctx.empty((B,), np.int32); fl = ctx.empty((B,), np.int32)
-    ctx.pnqp(dt, B, d, dev[0], dev[1], dev[2], dev[3], dxi, x, LU, piv, free, it, fl, int(n_iter),
-             _native.COUPLING_BATCH if coupling == "batch" else _native.COUPLING_ELEMENT)
+    try:
+        ctx.pnqp(dt, B, d, dev[0], dev[1], dev[2], dev[3], dxi, x, LU, piv, free, it, fl, int(n_iter),
+                 _native.COUPLING_BATCH if coupling == "batch" else _native.COUPLING_ELEMENT)
+    except _native.DiffMpcError as ex:
+        if not (auto and coupling == "batch" and "unsupported" in str(ex)):
+            raise
+        # 'auto' guessed that the batch is resident at once (one CTA / one cluster); the launcher knows better
+        ctx.pnqp(dt, B, d, dev[0], dev[1], dev[2], dev[3], dxi, x, LU, piv, free, it, fl, int(n_iter), _native.COUPLING_ELEMENT)
     its = it.download()
     if (fl.download() & _native.FLAG_QP_NOT_CONVERGED).any():
         warnings.warn("Projected Newton Quadratic Programming warning: Did not converge")   # pnqp.py:192

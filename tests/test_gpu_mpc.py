@@ -264,3 +264,48 @@ def test_bad_bounds_are_reported_through_the_c_abi(ctx):
         ctx.boxddp_solve(np.float64, T, B, n, m, ctx.to_device(x0), ctx.to_device(C), ctx.to_device(c), dlo, dhi,
                          _native.DYN_LINEAR, ctx.to_device(F), T - 1, None, None, ctx.zeros((T, B, m)), 1e-6, 1e-4, 0.2, 5, 5, 64,
                          _native.COUPLING_ELEMENT, *o)
+
+
+@pytest.mark.parametrize("n,m,B,T", [(8, 4, 100, 20), (4, 2, 700, 12), (3, 2, 300, 10), (3, 1, 2000, 20), (3, 1, 700, 20)])
+def test_batch_coupling_across_a_cluster(ctx, n, m, B, T):
+    """coupling = BATCH with more elements than one CTA holds: the batch is spread over the CTAs of one thread-block
+    cluster and PNQP's batch-global decisions (pnqp.py:139-144, 172-187) are OR-reduced through distributed shared memory
+    (csrc/common.cuh batch_or).  Against the oracle in the same (whole-batch) coupling: PNQP iteration counts, active sets
+    and line-search alphas bit-exact, values 1e-10."""
+    rs = np.random.RandomState(B + n)
+    s = n + m
+    bound = 0.4
+    C, c = psd_cost(rs, T, B, s)
+    F = stable_dynamics(rs, T, B, n, m, per_t=False)
+    f = 0.1 * rs.randn(T - 1, B, n)
+    x0 = rs.randn(B, n)
+    u_nom = np.clip(0.2 * rs.randn(T, B, m), -bound, bound)
+    lo = np.full((T, B, m), -bound); hi = np.full((T, B, m), bound)
+    x_nom = ompc.get_traj(x0, u_nom, ("linear", F, f))
+    g = dict(C=C, c=c, F=F, f=f, x_nom=x_nom, u_nom=u_nom, lower=lo, upper=hi, n=n, m=m)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ox, ou, fo, aux = ompc.step_forward(C, c, F, f, x_nom, u_nom, lo, hi, (C, c), ("linear", F, f), 0.2, 10, n, m,
+                                            need_expand=True, coupling="batch")
+    r, _ = run_mpc_forward(ctx, g, _native.COUPLING_BATCH)
+    assert np.array_equal(r["n_qp"], aux["n_qp"])
+    assert np.array_equal(r["free"].astype(float), aux["free"])
+    assert np.array_equal(r["alphas"], fo.alphas)
+    assert rel_err(r["Ks"], aux["Ks"]) < 1e-10 and rel_err(r["ks"], aux["ks"]) < 1e-10
+    assert rel_err(r["x"], ox) < 1e-10 and rel_err(r["u"], ou) < 1e-10
+    assert rel_err(r["costs"], fo.costs) < 1e-10
+    assert not r["flags"].any()
+
+
+def test_pnqp_batch_coupling_across_a_cluster(ctx):
+    rs = np.random.RandomState(77)
+    B, m = 2000, 4                      # 2000 x 4 lanes: ~14 CTAs of one cluster (112 registers -> 576 threads per CTA)
+    L = rs.randn(B, m, m)
+    H = L @ L.transpose(0, 2, 1) + 0.5 * np.eye(m)
+    q = 3 * rs.randn(B, m); lo = -rs.rand(B, m); hi = rs.rand(B, m)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ox, _, ofree, oit = opnqp.pnqp(H, q, lo, hi, coupling="batch")
+    x, LU, piv, free, it, fl = run_pnqp(ctx, H, q, lo, hi, coupling=_native.COUPLING_BATCH)
+    assert np.array_equal(free, ofree) and (it == int(oit)).all()
+    assert rel_err(x, ox) < 1e-10

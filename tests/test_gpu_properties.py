@@ -184,3 +184,43 @@ def test_c3_full_size_mpc_step_properties(ctx):
         du = (o_next["u"] - o["u"]).abs().amax(dim=(0, 2))
         o = o_next
     assert float((du < 1e-6).double().mean()) > 0.9
+
+
+def test_c5_forward_and_adjoint_are_deterministic(ctx):
+    """The n=32/m=8 kernels stream their tiles through single-buffered, just-in-time refilled shared memory (bulk copies
+    on the async proxy, cp.async, mbarriers).  Any ordering bug there shows up as a rare, non-reproducible corruption of
+    one element (round 2 found one: the C row-block refill could overtake the accumulator loads it follows, once per
+    ~1e6 element-steps).  The same inputs solved 40 times must give bit-identical gains, trajectories and gradients."""
+    T, B, n, m = 100, 1500, 32, 8
+    s = n + m
+    dev = torch.device("cuda", 0)
+    pr = lqr_problem(31, T, B, n, m)
+    d = {k: torch.from_numpy(pr[k]).to(dev) for k in ("x0", "C", "c", "F", "f")}
+    rs = np.random.RandomState(1)
+    gx = torch.from_numpy(rs.randn(T, B, n)).to(dev); gu = torch.from_numpy(rs.randn(T, B, m)).to(dev)
+    f64 = torch.float64
+    P = lambda t: t.data_ptr()
+
+    def outs():
+        return dict(x=torch.empty(T, B, n, dtype=f64, device=dev), u=torch.empty(T, B, m, dtype=f64, device=dev),
+                    Ks=torch.empty(T, B, m, n, dtype=f64, device=dev), ks=torch.empty(T, B, m, dtype=f64, device=dev),
+                    fac=torch.zeros(ctx.lqr_fac_elems(T, B, n, m), dtype=f64, device=dev),
+                    dx0=torch.empty(B, n, dtype=f64, device=dev), dC=torch.empty(T, B, s, s, dtype=f64, device=dev),
+                    dc=torch.empty(T, B, s, dtype=f64, device=dev), dF=torch.empty(T - 1, B, n, s, dtype=f64, device=dev),
+                    df=torch.empty(T - 1, B, n, dtype=f64, device=dev))
+    st = torch.cuda.Stream()
+
+    def run(o):
+        ctx.lqr_solve(np.float64, T, B, n, m, P(d["x0"]), P(d["C"]), P(d["c"]), P(d["F"]), T - 1, P(d["f"]), P(o["x"]),
+                      P(o["u"]), P(o["Ks"]), P(o["ks"]), P(o["fac"]), _native.LQR_FACTOR | _native.LQR_ROLLOUT | _native.LQR_SAVE_FAC,
+                      st.cuda_stream)
+        ctx.lqr_adjoint(np.float64, T, B, n, m, P(d["C"]), P(d["c"]), P(d["F"]), P(o["x"]), P(o["u"]), P(gx), P(gu), P(o["Ks"]),
+                        P(o["fac"]), P(o["dx0"]), P(o["dC"]), P(o["dc"]), P(o["dF"]), P(o["df"]), _native.ADJ_STRICT_REFERENCE,
+                        st.cuda_stream)
+        torch.cuda.synchronize()
+    ref, o = outs(), outs()
+    run(ref)
+    for it in range(40):
+        run(o)
+        for k in ("Ks", "ks", "x", "u", "dx0", "dC", "dc", "dF", "df"):
+            assert torch.equal(o[k], ref[k]), (it, k)
