@@ -565,7 +565,9 @@ def run_b200(args):
                  "role": ("adjoint sweep 2 (t up): d-tau rollout fused with lambda = V x + v, d-lambda = V dx + v' and " if fused_adj
                           else "lambda / d-lambda recursions + ") + "dC, dc, dF, df, dx0 (carries the adjoint's algorithmic bytes; "
                          "the pair takes %.3f ms)" % kt["adjoint"]}}
-        extra_kernels = {"lqr_dtau_kernel+adjoint_out_kernel<REDUCE_TB>+reduce_partials_kernel": {
+        red_name = ("lqr_dtau_kernel<FUSED>+adjoint_fused_kernel<REDUCE_TB>+reduce_partials_kernel" if fused_adj else
+                    "lqr_dtau_kernel+adjoint_out_kernel<REDUCE_TB>+reduce_partials_kernel")
+        extra_kernels = {red_name: {
             "ms": kt["adjoint_reduced"], "role": "KKT adjoint with the (T,B)-sum of dC,dc,dF,df fused in (shared-parameter "
             "models; not part of the timed step, which materialises the full gradients as the reference does)"}}
         for name, k in kernels.items():

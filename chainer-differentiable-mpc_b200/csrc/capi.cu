@@ -74,19 +74,25 @@ static int lqr_adjoint_impl(dmpc_handle h, int T, int B, int n, int m, const voi
   d.F = (const R*)F; d.gx = (const R*)gx; d.gu = (const R*)gu; d.Ks = (const R*)Ks; d.fac = (const R*)fac;
   d.dc = (R*)dc;
   int rc = DMPC_OK;
-  if (!partials && df && adjoint_fused_available(n, m)) {
-    // two sweeps: v'_t is parked in the df output buffer (row t-1) and in dx0 (t = 0) between them
-    d.vp = (R*)df; d.dx0 = (R*)dx0;
+  if ((partials || df) && adjoint_fused_available(n, m)) {
+    // two sweeps.  Full gradients: v'_t is parked in the df output buffer (row t-1) and in dx0 (t = 0) between them.
+    // Fused (T,B)-reduction: dc is a workspace, v'_t travels in its first n entries, nothing but dx0 and the per-element
+    // partial sums is written.
+    d.vp = partials ? nullptr : (R*)df; d.dx0 = (R*)dx0;
     AdjFusedParams<R> a;
     memset(&a, 0, sizeof(a));
     a.T = T; a.B = B; a.n = n; a.m = m;
     a.flags = (flags & DMPC_ADJ_STRICT_REFERENCE) ? (ADJ_QUIRK_DC | ADJ_QUIRK_DF) : 0;
     a.F = (const R*)F; a.Ks = (const R*)Ks; a.Vv = (const R*)fac + (size_t)T * B * fac_elems_per_step(n, m);
     a.x = (const R*)x; a.u = (const R*)u; a.vp = (const R*)df; a.dx0 = (const R*)dx0;
-    a.dc = (R*)dc; a.dC = (R*)dC; a.dF = (R*)dF; a.df = (R*)df;
+    a.dc = (R*)dc; a.dC = (R*)dC; a.dF = (R*)dF; a.df = (R*)df; a.red = (R*)partials;
     const int stage = (flags & DMPC_ADJ_STAGE_OUT_ONLY) ? 2 : ((flags & DMPC_ADJ_STAGE_DTAU_ONLY) ? 1 : 0);
     rc = launch_adjoint_fused<R>(d, a, stage, st, &h->launches);
-    if (rc) h->err = "adjoint_fused launch failed";
+    if (rc) { h->err = "adjoint_fused launch failed"; return rc; }
+    if (partials && stage != 1) {
+      rc = launch_reduce_partials<R>((const R*)partials, B, adj_red_elems(n, m), (R*)sums, st, &h->launches);
+      if (rc) h->err = "reduce_partials launch failed";
+    }
     return rc;
   }
   if (!(flags & DMPC_ADJ_STAGE_OUT_ONLY)) {

@@ -32,8 +32,9 @@ struct AdjFusedParams {
   const R* vp;                  // [T-1,B,n] row t-1 = v'_t (t >= 1) from adjoint sweep 1; MAY ALIAS df: row t is consumed
                                 //           (cp.async of stage t) before df_t is written in step t
   const R* dx0;                 // [B,n]    v'_0 = dlambda_0 (already the final dx0 output)
-  R* dc;                        // [T,B,s]  in: k'_t in [.., n:]   out: dtau_t
+  R* dc;                        // [T,B,s]  in: k'_t in [.., n:]   out: dtau_t (RED: in only, v'_t in [.., :n])
   R* dC; R* dF; R* df;          // outputs (df nullable)
+  R* red;                       // RED: [B][s*s + s + n*s + n] per-element sums over t (dC | dc | dF | df), nothing else written
 };
 
 struct AdjFusedLayout { int oF, oK, oV, ov, oxn, otau, okp, ovpn, stage, st0, st1, dtau, dxn, lam, dlam, dlamp, total; };
@@ -80,7 +81,10 @@ __device__ __forceinline__ R quad_dot(const R* row, const R* vec, int K, int q, 
   return a;
 }
 
-template <typename R, int N, int M, int G>
+// RED = ADJ_REDUCE_TB: the per-step outer products are summed over t in registers (every output (i,j) is owned by one thread
+// for the whole horizon) and one record per element is written for reduce_partials_kernel; dC, dc, dF, df are never
+// materialised and v'_t travels in the first n entries of the d-tau workspace (which is then input only).
+template <typename R, int N, int M, int G, bool RED = false>
 __global__ void __launch_bounds__(G) adjoint_fused_kernel(AdjFusedParams<R> p) {
   static_assert(N % 4 == 0 && M % 4 == 0 && G % 32 == 0, "quad-split dots");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -109,10 +113,22 @@ __global__ void __launch_bounds__(G) adjoint_fused_kernel(AdjFusedParams<R> p) {
       g_cp_async(g, base + L.oF, p.F + idx * n * s, n * s);
       g_cp_async(g, base + L.oV, p.Vv + idn * (n * n + n), n * n + n);
       g_cp_async(g, base + L.oxn, p.x + idn * n, n);
-      g_cp_async(g, base + L.ovpn, p.vp + idx * n, n);
+      if (RED) g_cp_async(g, base + L.ovpn, p.dc + idn * s, n);
+      else g_cp_async(g, base + L.ovpn, p.vp + idx * n, n);
     }
     cp_async_commit();
   };
+  constexpr int NR = G / s;
+  static_assert(NR >= 1 && G >= s, "one column per thread");
+  constexpr int KC = (s + NR - 1) / NR, KF = (n + NR - 1) / NR;
+  const int tj = g.lane % s, ti = g.lane / s;
+  R accC[RED ? KC : 1], accF[RED ? KF : 1], accc = R(0), accf = R(0);
+  if (RED) {
+#pragma unroll
+    for (int k = 0; k < KC; ++k) accC[k] = R(0);
+#pragma unroll
+    for (int k = 0; k < KF; ++k) accF[k] = R(0);
+  }
   load_tiles(0, 0);
   for (int o = g.lane; o < n; o += G) { dtau[o] = R(0); dlamp[o] = p.dx0[(size_t)e * n + o]; }   // dx_0 = 0, dlambda_0 = v'_0
   int st = 0;
@@ -145,27 +161,52 @@ __global__ void __launch_bounds__(G) adjoint_fused_kernel(AdjFusedParams<R> p) {
     auto tau = [&](int j) -> R { return j < n ? xt[j] : ut[j - n]; };
     // thread (ti, tj) owns column tj of the rows ti, ti + NR, ...: tau_j, dtau_j stay in registers and the row operands
     // are warp broadcasts (2 shared-memory reads per output instead of 4, no bank conflicts); rows are written whole
-    constexpr int NR = G / s;
-    static_assert(NR >= 1, "one column per thread");
-    const int tj = g.lane % s, ti = g.lane / s;
     if (ti < NR) {
       const R tau_j = tau(tj), dt_j = dtau[tj];
-      R* dCg = p.dC + idx * s * s + tj;
-      for (int i = ti; i < s; i += NR) {
-        const R a = dtau[i] * tau_j, b = tau(i) * dt_j;
-        dCg[i * s] = quirk_dC ? (R(0.5) * a + b) : (R(0.5) * (a + b));
+      R* dCg = RED ? nullptr : p.dC + idx * s * s + tj;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int i = ti + k * NR;
+        if (i < s) {
+          const R a = dtau[i] * tau_j, b = tau(i) * dt_j;
+          const R v = quirk_dC ? (R(0.5) * a + b) : (R(0.5) * (a + b));
+          if (RED) accC[k] += v; else dCg[i * s] = v;
+        }
       }
       if (more) {
-        R* dFg = p.dF + idx * n * s + tj;
-        for (int i = ti; i < n; i += NR) dFg[i * s] = dlam[i] * tau_j + lam[i] * dt_j;
+        R* dFg = RED ? nullptr : p.dF + idx * n * s + tj;
+#pragma unroll
+        for (int k = 0; k < KF; ++k) {
+          const int i = ti + k * NR;
+          if (i < n) {
+            const R v = dlam[i] * tau_j + lam[i] * dt_j;
+            if (RED) accF[k] += v; else dFg[i * s] = v;
+          }
+        }
       }
     }
-    for (int o = g.lane; o < s; o += G) p.dc[idx * s + o] = dtau[o];
-    if (more && p.df) for (int o = g.lane; o < n; o += G) p.df[idx * n + o] = quirk_df ? dlamp[o] : dlam[o];
+    if (RED) {
+      if (g.lane < s) accc += dtau[g.lane];
+      if (more && g.lane < n) accf += quirk_df ? dlamp[g.lane] : dlam[g.lane];
+    } else {
+      for (int o = g.lane; o < s; o += G) p.dc[idx * s + o] = dtau[o];
+      if (more && p.df) for (int o = g.lane; o < n; o += G) p.df[idx * n + o] = quirk_df ? dlamp[o] : dlam[o];
+    }
     g.sync();
     if (more) for (int o = g.lane; o < n; o += G) { dtau[o] = dxn[o]; dlamp[o] = dlam[o]; }
     g.sync();
     st ^= 1;
+  }
+  if (RED) {
+    R* out = p.red + (size_t)e * (s * s + s + n * s + n);
+    if (ti < NR) {
+#pragma unroll
+      for (int k = 0; k < KC; ++k) { const int i = ti + k * NR; if (i < s) out[i * s + tj] = accC[k]; }
+#pragma unroll
+      for (int k = 0; k < KF; ++k) { const int i = ti + k * NR; if (i < n) out[s * s + s + i * s + tj] = accF[k]; }
+    }
+    if (g.lane < s) out[s * s + g.lane] = accc;
+    if (g.lane < n) out[s * s + s + n * s + g.lane] = accf;
   }
 }
 

@@ -296,7 +296,8 @@ struct DtauParams {
   const R* Ks;   // [T,B,m,n]
   const R* fac;  // [T,B,m*m+n*m]
   R* dc;         // [T,B,s]  out: dtau
-  R* vp;         // FUSED: [T-1,B,n] out: v'_t for t >= 1 at row t-1 (the caller parks it in the df output buffer)
+  R* vp;         // FUSED: [T-1,B,n] out: v'_t for t >= 1 at row t-1 (the caller parks it in the df output buffer);
+                 //        nullptr -> v'_t goes to dc[t,b,:n] instead (the fused-reduction adjoint, where dc is a workspace)
   R* dx0;        // FUSED: [B,n] out: v'_0 = dlambda_0
 };
 
@@ -386,7 +387,7 @@ __global__ void lqr_dtau_kernel(DtauParams<R> p) {
       if (valid) for (int o = g.lane; o < m; o += G) p.dc[((size_t)t * tb + e) * s + n + o] = kp[o];
       g.sync();
       if (FUSED && valid) {
-        R* dst = t > 0 ? p.vp + ((size_t)(t - 1) * tb + e) * n : p.dx0 + (size_t)e * n;
+        R* dst = t == 0 ? p.dx0 + (size_t)e * n : (p.vp ? p.vp + ((size_t)(t - 1) * tb + e) * n : p.dc + ((size_t)t * tb + e) * s);
         for (int o = g.lane; o < n; o += G) dst[o] = vp[o];
       }
       st ^= 1;

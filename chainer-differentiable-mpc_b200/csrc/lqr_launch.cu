@@ -105,7 +105,8 @@ int launch_adjoint_fused(const DtauParams<R>& d, const AdjFusedParams<R>& a, int
     if (stage != 2) rc = do_launch(lqr_dtau_kernel<R, N_, M_, 64, true>, d, 64, (size_t)L1.stride * sizeof(R), d.B, st, nl); \
     if (rc || stage == 1) return rc;                                                                                  \
     const AdjFusedLayout L2 = adj_fused_layout<R>(N_, M_);                                                            \
-    return do_launch(adjoint_fused_kernel<R, N_, M_, 128>, a, 128, (size_t)L2.total * sizeof(R), a.B, st, nl);        \
+    if (a.red) return do_launch(adjoint_fused_kernel<R, N_, M_, 128, true>, a, 128, (size_t)L2.total * sizeof(R), a.B, st, nl); \
+    return do_launch(adjoint_fused_kernel<R, N_, M_, 128, false>, a, 128, (size_t)L2.total * sizeof(R), a.B, st, nl); \
   }
   DMPC_FUSED_SHAPES(X)
 #undef X

@@ -107,12 +107,21 @@ class BoxDDP(LinkBase):
         coupling = resolve_coupling(self.coupling, B, n, m)
         o = dict(x=ctx.empty((T, B, n), dt), u=ctx.empty((T, B, m), dt), costs=ctx.empty((B,), dt),
                  du=ctx.empty((B,), dt), du_last=ctx.empty((B,), dt))
-        n_iter, status, flags = ctx.boxddp_solve(
-            dt, T, B, n, m, ctx.to_device(x_init), ctx.to_device(C_arr), ctx.to_device(c_arr), ctx.to_device(self.u_lower),
-            ctx.to_device(self.u_upper), dyn, dF, F_T, df, params, ctx.to_device(u), self.eps, self.best_cost_eps,
-            self.ls_decay, self.not_improved_lim, self.max_iter, MAX_LS_TRIALS,
-            _native.COUPLING_BATCH if coupling == "batch" else _native.COUPLING_ELEMENT,
-            o["x"], o["u"], o["costs"], o["du"], o["du_last"], F_lin, f_lin)
+        dev_in = [ctx.to_device(a) for a in (x_init, C_arr, c_arr, self.u_lower, self.u_upper, u)]
+
+        def solve(cpl):
+            return ctx.boxddp_solve(
+                dt, T, B, n, m, dev_in[0], dev_in[1], dev_in[2], dev_in[3], dev_in[4], dyn, dF, F_T, df, params, dev_in[5],
+                self.eps, self.best_cost_eps, self.ls_decay, self.not_improved_lim, self.max_iter, MAX_LS_TRIALS,
+                _native.COUPLING_BATCH if cpl == "batch" else _native.COUPLING_ELEMENT,
+                o["x"], o["u"], o["costs"], o["du"], o["du_last"], F_lin, f_lin)
+        try:
+            n_iter, status, flags = solve(coupling)
+        except _native.DiffMpcError as ex:      # 'auto' guessed the batch is resident at once; the launcher knows better
+            from mpc_step import DEFAULT_COUPLING
+            if not ((self.coupling or DEFAULT_COUPLING) == "auto" and coupling == "batch" and "unsupported" in str(ex)):
+                raise
+            n_iter, status, flags = solve("element")
         if flags & _native.FLAG_QP_NOT_CONVERGED:
             warnings.warn("Projected Newton Quadratic Programming warning: Did not converge")
         if flags & _native.FLAG_LS_CAPPED:
