@@ -1056,7 +1056,10 @@ def il_iteration(B=8192, reps=3, dist=None, dev=None, rank=0, world=1, local=0):
                            % (B, world, "NCCL" if dist is not None else "single rank: no exchange"),
                  "n_gpus": world, "global_batch": B * world,
                  "mpc_solves_per_sec": world * B / (best["total_ms"] * 1e-3), "grad_q_finite": bool(np.isfinite(dq).all()),
-                 "grad_p_finite": bool(np.isfinite(dp).all()), "timing": "max over ranks of the best of %d iterations" % reps})
+                 "grad_p_finite": bool(np.isfinite(dp).all()), "timing": "max over ranks of the best of %d iterations" % reps,
+                 "allreduce_note": "allreduce_ms is the time spent inside the call = wait for the slowest rank's solve (the ranks "
+                                   "hold different instances and share the host's cores) + the transfer; the transfer alone is "
+                                   "param_grad_exchange.allreduce_ms"})
     return best
 
 

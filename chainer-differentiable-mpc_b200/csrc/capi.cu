@@ -129,7 +129,7 @@ static int mpc_forward_impl(dmpc_handle h, int T, int B, int n, int m, const voi
   MpcFwdParams<R> p;
   memset(&p, 0, sizeof(p));
   p.T = T; p.B = B; p.n = n; p.m = m; p.F_T = F_T; p.need_expand = need_expand; p.dynamics = dynamics;
-  p.coupling = coupling; p.max_ls_trials = max_ls_trials > 0 ? max_ls_trials : 64; p.n_qp_iter = 20;
+  p.coupling = coupling; p.max_ls_trials = max_ls_trials > 0 ? max_ls_trials : (max_ls_trials < 0 ? -1 : 64); p.n_qp_iter = 20;
   p.ls_decay = (R)ls_decay;
   p.C = (const R*)C; p.c = (const R*)c; p.F = (const R*)F; p.f = (const R*)f;
   p.x_nom = (const R*)x_nom; p.u_nom = (const R*)u_nom; p.lo = (const R*)lo; p.hi = (const R*)hi;
@@ -463,10 +463,11 @@ int dmpc_mpc_step_forward(dmpc_handle h, int dtype, int T, int B, int n, int m, 
   if (!h) return DMPC_ERR_NULL;
   if (T < 1 || B < 1 || n < 1 || m < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "T,B,n,m must be >= 1");
   if (T > 1 && F_T != T - 1 && F_T != T) return fail(h, DMPC_ERR_BAD_SHAPE, "F_hat must have T-1 or T time rows");
-  if (!d_C || !d_c || (T > 1 && !d_F) || !d_x_nom || !d_u_nom || !d_lower || !d_upper || !d_tC || !d_tc || !d_x || !d_u ||
-      !d_Ks || !d_ks || !d_costs || !d_alphas)
+  const bool sweep_only = max_ls_trials < 0;     // backward_rec only (Ks, ks, n_qp, free, flags): host-side line search
+  if (!d_C || !d_c || (T > 1 && !d_F) || !d_x_nom || !d_u_nom || !d_lower || !d_upper || !d_Ks || !d_ks ||
+      (!sweep_only && (!d_tC || !d_tc || !d_x || !d_u || !d_costs || !d_alphas)))
     return fail(h, DMPC_ERR_NULL, "mpc_step_forward: required buffer is NULL");
-  if (dynamics == DMPC_DYN_LINEAR && T > 1 && !d_tF) return fail(h, DMPC_ERR_NULL, "linear true dynamics need d_tF");
+  if (!sweep_only && dynamics == DMPC_DYN_LINEAR && T > 1 && !d_tF) return fail(h, DMPC_ERR_NULL, "linear true dynamics need d_tF");
   if (dynamics == DMPC_DYN_PENDULUM && (n != 3 || m != 1 || !h_dyn_params)) return fail(h, DMPC_ERR_BAD_SHAPE, "pendulum dynamics: n=3, m=1, params required");
   if (dynamics != DMPC_DYN_LINEAR && dynamics != DMPC_DYN_PENDULUM) return fail(h, DMPC_ERR_UNSUPPORTED, "dynamics selector");
   if (set_dev(h)) return DMPC_ERR_CUDA;

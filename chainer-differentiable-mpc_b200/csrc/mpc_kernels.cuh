@@ -444,6 +444,10 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
   }
 
   if (BATCH) batch_or_finish();      // last batch-wide decision is behind us: other CTAs of the cluster may exit
+  if (p.max_ls_trials < 0) {         // backward_rec only: the caller runs the line search on the host (Python callables)
+    if (valid && g.lane == 0 && p.flags) p.flags[e] = status;
+    return;
+  }
 
   // =========================== forward_rec (mpc_step.py:175-286) ===========================
   // pass -1 evaluates the cost of the nominal trajectory (xpget_cost, :191); passes >= 0 are the

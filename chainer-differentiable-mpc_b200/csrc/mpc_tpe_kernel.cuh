@@ -192,6 +192,10 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
     }
   }
   if (BATCH) batch_or_finish();                             // the last batch-wide decision is behind us
+  if (p.max_ls_trials < 0) {                                // backward_rec only: the line search runs on the host
+    if (writer && p.flags) p.flags[e] = status;
+    return;
+  }
   if (NA > 1) __syncwarp();                                 // K_t, k_t of lane a = 0 are visible to its candidate lanes
   else if (!valid) return;                                  // padding threads were only needed for the PNQP barriers
 

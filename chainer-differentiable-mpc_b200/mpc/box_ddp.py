@@ -4,8 +4,8 @@
     x, u, costs = solver((x_init, QuadCost(C, c), dynamics))
 
 Per iteration (reference :121-230): rollout of the nominal controls (`dmpc_get_traj`), linearisation
-(LinDx: as given; pendulum: analytic Jacobian on the device, replacing approximate.linearize_dynamics),
-one fused MPC step (`dmpc_mpc_step_forward`), then the reference's bookkeeping: per-element best
+(LinDx: as given; pendulum: analytic Jacobian on the device, replacing approximate.linearize_dynamics; any other
+callable: approximate.linearize_dynamics / approximate_cost on the host, then MPCstep's plugin path), one fused MPC step (`dmpc_mpc_step_forward`), then the reference's bookkeeping: per-element best
 trajectory (vectorised instead of the Python loop over B at :200-209, same semantics), global exits on
 max(full_du_norm) < eps and on the shared n_not_improved counter, and the final no-op MPCstep whose
 backward is the gradient path (:247-259).  The batch-coupled quirks (H2 iii, iv) are kept on the host.
@@ -83,7 +83,12 @@ class BoxDDP(LinkBase):
             ctx.get_traj(dt, T, B, n, m, _native.DYN_PENDULUM, ctx.to_device(x_init), ctx.to_device(u), None, None,
                          pendulum_params(dynamics), dx, Fo, fo)
             return dx.download(), Fo.download()[:T - 1], fo.download()[:T - 1]
-        raise NotImplementedError("dynamics must be util.LinDx or a PendulumDx (SURVEY.md H3)")
+        # plugin: roll out and linearise through the Python callable on the host (reference :123, :129)
+        from approximate import linearize_dynamics
+        from util import xpget_traj
+        x = xpget_traj(T, u, x_init, dynamics)
+        F, f = linearize_dynamics(x, u, dynamics)
+        return np.asarray(x, dtype=dt), as_f(F, dt), as_f(f, dt)
 
     def _solve_on_device(self, ctx, x_init, C_arr, c_arr, true_dyn, u):
         """The loop of reference :121-230 in one C-ABI call.  Returns (best, du_last, n_iter, status, F_lin, f_lin)."""
@@ -138,8 +143,12 @@ class BoxDDP(LinkBase):
         T, B, n, m = self.T, self.n_batch, self.n_state, self.n_ctrl
         x_init = as_f(x_init, np.float64)
         assert list(x_init.shape) == [B, n], " x_init dim mismatch"
-        if not isinstance(cost, QuadCost):
-            raise NotImplementedError("cost must be a util.QuadCost")
+        quad = isinstance(cost, QuadCost)
+        if not quad and not callable(cost):
+            raise TypeError("cost must be a util.QuadCost or a callable tau[B,s] -> cost[B]")
+        plugin = not quad or not (isinstance(dynamics, LinDx) or is_pendulum(dynamics))
+        if plugin and not (isinstance(dynamics, LinDx) or callable(dynamics)):
+            raise TypeError("dynamics must be a util.LinDx, a PendulumDx or a callable (x[B,n], u[B,m]) -> x_next[B,n]")
         ctx = _native.default_context(self.device)
         if self.u_init is None:
             u = np.zeros((T, B, m))
@@ -149,8 +158,12 @@ class BoxDDP(LinkBase):
                 u = np.repeat(u[:, None, :], B, axis=1)
         assert list(u.shape) == [T, B, m], "u dim mismatch, actual" + str(u.shape)
         assert not np.isnan(u).any()
-        C_arr, c_arr = as_f(cost.C, np.float64), as_f(cost.c, np.float64)
-        true_cost = QuadCost(C_arr, c_arr)
+        if quad:
+            C_arr, c_arr = as_f(cost.C, np.float64), as_f(cost.c, np.float64)
+            true_cost = QuadCost(C_arr, c_arr)
+        else:
+            from approximate import approximate_cost
+            true_cost = cost
         if isinstance(dynamics, LinDx):
             true_dyn = LinDx(as_f(dynamics.F, np.float64), None if to_xp(dynamics.f) is None else as_f(dynamics.f, np.float64))
         else:
@@ -160,13 +173,15 @@ class BoxDDP(LinkBase):
         for_out = None
         status = "max_iter"
         n_iter = 0
-        on_device = self.device_loop and not self.verbose and not self.ilqr_verbose
+        on_device = self.device_loop and not self.verbose and not self.ilqr_verbose and not plugin
         if on_device:
             best, du_last, n_iter, status, large_f, f = self._solve_on_device(ctx, x_init, C_arr, c_arr, true_dyn, u)
             print({"converged": "Converged", "not_improved": "Not improved lim", "max_iter": "Not Converged "}[status])
         for i in range(0 if on_device else self.max_iter):
             n_iter = i + 1
             x, large_f, f = self._rollout(ctx, x_init, u, true_dyn)
+            if not quad:                                                            # reference :133-136
+                C_arr, c_arr = (as_f(v, np.float64) for v in approximate_cost(x, u, cost)[:2])
             step = MPCstep(controls=u, T=T, u_upper=self.u_upper, u_lower=self.u_lower, n_batch=B, n_state=n,
                            n_ctrl=m, current_states=x, true_cost=true_cost, true_dynamics=true_dyn,
                            ls_decay=self.ls_decay, max_ls_iter=self.max_ls_iter, verbose=self.ilqr_verbose,
@@ -202,6 +217,8 @@ class BoxDDP(LinkBase):
         if not on_device:
             _, large_f, f = self._rollout(ctx, x[0], u, true_dyn)
             du_last = for_out.full_du_norm
+            if not quad:                                                            # reference :241-242
+                C_arr, c_arr = (as_f(v, np.float64) for v in approximate_cost(x, u, cost)[:2])
         final = MPCstep(controls=u, T=T, u_upper=self.u_upper, u_lower=self.u_lower, n_batch=B, n_state=n, n_ctrl=m,
                         current_states=x, true_cost=true_cost, true_dynamics=true_dyn, ls_decay=self.ls_decay,
                         max_ls_iter=self.max_ls_iter, verbose=self.ilqr_verbose, need_expand=True,
@@ -213,7 +230,7 @@ class BoxDDP(LinkBase):
         if self.update_dynamics:                                                   # reference :252-258
             C_in, c_in = C_arr, c_arr
         else:
-            C_in, c_in = cost.C, cost.c
+            C_in, c_in = (cost.C, cost.c) if quad else (wrap(C_arr), wrap(c_arr))
             F_in, f_in = to_xp(F_in), to_xp(f_in)
         out = final.apply((x[0].copy(), C_in, c_in, F_in, f_in))
         x_new, u_new = out[0], out[1]

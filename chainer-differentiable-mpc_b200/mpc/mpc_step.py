@@ -5,10 +5,11 @@ forward  (reference :288-328): Taylor shift + bounded Riccati sweep with one PNQ
 backward (reference :330-460): active-set LQR (LQR_active) + lambda/d-lambda recursions + outer
           products - three launches (`dmpc_mpc_step_backward`).
 
-Supported true_cost: util.QuadCost.  Supported true_dynamics: util.LinDx, or a pendulum object
-(the reference's env_dx.pendulum.PendulumDx or pendulum_dx.PendulumDx of this package), whose step
-and analytic Jacobian are device code.  Other Python callables cannot run inside a fused kernel
-and raise NotImplementedError.
+Fused path: true_cost = util.QuadCost and true_dynamics = util.LinDx or a pendulum object (the reference's
+env_dx.pendulum.PendulumDx or pendulum_dx.PendulumDx of this package), whose step and analytic Jacobian are device
+code.  Plugin path: any other Python callable (cost: tau [B,s] -> [B]; dynamics: (x [B,n], u [B,m]) -> [B,n]) cannot
+run inside a kernel, so backward_rec still runs on the GPU (the same kernel, max_ls_trials < 0 = "sweep only") and the
+line search of forward_rec (:175-286) runs on the host through the callable, as the reference does.
 
 The batch-scrambled `full_du_norm` / `alpha_du_norm` (reference :261-263, :275-277) are reproduced
 bit-faithfully on the host from the kernel's alpha=1 controls.
@@ -132,8 +133,8 @@ class MPCstep(FunctionNodeBase):
         lo, hi = as_f(self.u_lower, dt), as_f(self.u_upper, dt)
         assert not np.isnan(u_nom).any() and not np.isnan(lo).any() and not np.isnan(hi).any()
         assert (lo <= hi).all(), " lower is larger than upper"
-        if not isinstance(self.true_cost, QuadCost):
-            raise NotImplementedError("true_cost must be a util.QuadCost (callable costs cannot run in the fused kernel)")
+        if self._is_plugin():
+            return self._forward_plugin(C_hat, c_hat, F_hat, f_hat, x_nom, u_nom, lo, hi)
         tC, tc = as_f(self.true_cost.C, dt), as_f(self.true_cost.c, dt)
         # host -> device: every input that is not an alias of another one; small problems go through ONE packed copy
         ins = {"C": C_hat, "c": c_hat, "F": F_hat, "x_nom": x_nom, "u_nom": u_nom, "lo": lo, "hi": hi}
@@ -151,11 +152,9 @@ class MPCstep(FunctionNodeBase):
                 ins["tF"] = tF
             if tf is not None:
                 ins["tf"] = tf
-        elif is_pendulum(self.true_dynamics):
+        else:
             dyn, params = _native.DYN_PENDULUM, pendulum_params(self.true_dynamics)
             tf = None
-        else:
-            raise NotImplementedError("true_dynamics must be util.LinDx or a PendulumDx (SURVEY.md H3)")
         out_specs = [("x", (T, B, n), dt), ("u", (T, B, m), dt), ("Ks", (T, B, m, n), dt), ("ks", (T, B, m), dt),
                      ("u_first", (T, B, m), dt), ("objs", (T, B), dt), ("costs", (B,), dt), ("old", (B,), dt),
                      ("alphas", (B,), dt), ("n_qp", (T, B), np.int32), ("free", (T, B, m), np.uint8),
@@ -206,6 +205,112 @@ class MPCstep(FunctionNodeBase):
                                  scrambled_norm(u_nom - u, B, T, m), np.mean(r["alphas"]), r["costs"])
         self.aux = dict(Ks=r["Ks"], ks=r["ks"], alphas=r["alphas"], free=r["free"], n_qp=r["n_qp"], n_ls=r["n_ls"],
                         old_costs=r["old"], coupling=coupling, u_first=r["u_first"])
+        return x, u
+
+    # ---- plugin path: Python-callable true cost / dynamics ------------------------------------
+    def _is_plugin(self):
+        if not isinstance(self.true_cost, QuadCost):
+            if not callable(self.true_cost):
+                raise TypeError("true_cost must be a util.QuadCost or a callable tau[B,s] -> cost[B]")
+            return True
+        if isinstance(self.true_dynamics, LinDx) or is_pendulum(self.true_dynamics):
+            return False
+        if not callable(self.true_dynamics):
+            raise TypeError("true_dynamics must be a util.LinDx, a PendulumDx or a callable (x[B,n], u[B,m]) -> x_next[B,n]")
+        return True
+
+    def _stage_cost(self, t, tau):
+        if isinstance(self.true_cost, QuadCost):                     # reference :245-251
+            C, c = np.asarray(to_xp(self.true_cost.C)), np.asarray(to_xp(self.true_cost.c))
+            return 0.5 * np.einsum("bi,bij,bj->b", tau, C[t], tau) + np.einsum("bi,bi->b", tau, c[t])
+        return np.asarray(to_xp(self.true_cost(tau)), dtype=np.float64)
+
+    def _true_step(self, t, x, u):
+        if isinstance(self.true_dynamics, LinDx):                    # reference :229-236
+            Fm, f = np.asarray(to_xp(self.true_dynamics.F)), to_xp(self.true_dynamics.f)
+            nx = np.einsum("bij,bj->bi", Fm[t], np.concatenate((x, u), axis=1))
+            return nx if f is None else nx + np.asarray(f)[t]
+        return np.asarray(to_xp(self.true_dynamics(x, u)), dtype=np.float64)      # :237-240
+
+    def _host_line_search(self, Ks, ks, x_nom, u_nom, lo, hi):
+        """forward_rec (reference :175-286) for callables: per-element alpha, every pass re-rolls the horizon through
+        the callable for the whole batch; elements whose cost already dropped keep their alpha, so their rows repeat."""
+        T, B, m = self.T, self.n_batch, self.n_ctrl
+        old = sum(self._stage_cost(t, np.concatenate((x_nom[t], u_nom[t]), axis=1)) for t in range(T))
+        alphas = np.ones(B)
+        u_first = None
+        n_ls = np.ones(B, dtype=np.int32)               # passes each element needed (the kernel's d_n_ls)
+        capped = np.zeros(B, dtype=bool)
+        trial = 0
+        while True:
+            xs, us, objs = [x_nom[0]], [], []
+            dx = np.zeros_like(x_nom[0])
+            for t in range(T):
+                ut = np.einsum("bij,bj->bi", Ks[t], dx) + u_nom[t] + alphas[:, None] * ks[t]
+                assert np.isfinite(ut).all()
+                ut = np.minimum(np.maximum(ut, lo[t]), hi[t])
+                us.append(ut)
+                objs.append(self._stage_cost(t, np.concatenate((xs[t], ut), axis=1)))
+                if t < T - 1:
+                    nx = self._true_step(t, xs[t], ut)
+                    assert not np.isnan(nx).any()
+                    xs.append(nx)
+                    dx = nx - x_nom[t + 1]
+            cur = np.sum(np.stack(objs), axis=0)
+            if u_first is None:
+                u_first = np.stack(us)
+            worse = cur > old
+            trial += 1
+            if not worse.any():
+                break
+            if trial >= MAX_LS_TRIALS:          # same cap as the kernel: alpha stays the one of the last pass
+                capped = worse
+                break
+            alphas[worse] *= self.ls_decay
+            n_ls[worse] += 1
+        return np.stack(xs), np.stack(us), np.stack(objs), cur, old, alphas, u_first, n_ls, capped
+
+    def _forward_plugin(self, C_hat, c_hat, F_hat, f_hat, x_nom, u_nom, lo, hi):
+        T, B, n, m = self.T, self.n_batch, self.n_state, self.n_ctrl
+        ctx, dt = self._ctx, C_hat.dtype
+        ins = {"C": C_hat, "c": c_hat, "F": F_hat, "x_nom": x_nom, "u_nom": u_nom, "lo": lo, "hi": hi}
+        if not (f_hat is None or self.need_expand):
+            ins["f"] = f_hat[:T - 1]
+        d = {k: ctx.to_device(a) for k, a in ins.items()}
+        o = {k: ctx.empty(shape, t) for k, shape, t in
+             [("Ks", (T, B, m, n), dt), ("ks", (T, B, m), dt), ("n_qp", (T, B), np.int32), ("free", (T, B, m), np.uint8),
+              ("flags", (B,), np.int32)]}
+        coupling = resolve_coupling(self.coupling, B, n, m)
+
+        def launch(cpl):
+            ctx.mpc_step_forward(dt, T, B, n, m, d["C"], d["c"], d["F"], F_hat.shape[0], d.get("f"), d["x_nom"], d["u_nom"],
+                                 d["lo"], d["hi"], None, None, _native.DYN_LINEAR, None, None, None, self.ls_decay,
+                                 -1, self.need_expand,
+                                 _native.COUPLING_BATCH if cpl == "batch" else _native.COUPLING_ELEMENT,
+                                 None, None, o["Ks"], o["ks"], None, None, None, None, None, o["n_qp"], o["free"], None,
+                                 o["flags"])
+        try:
+            launch(coupling)
+        except _native.DiffMpcError as ex:
+            if not ((self.coupling or DEFAULT_COUPLING) == "auto" and coupling == "batch" and "unsupported" in str(ex)):
+                raise
+            coupling = "element"
+            launch(coupling)
+        r = {k: v.download() for k, v in o.items()}
+        if (r["flags"] & _native.FLAG_QP_NOT_CONVERGED).any():
+            warnings.warn("Projected Newton Quadratic Programming warning: Did not converge")
+        f64 = np.float64
+        x, u, objs, costs, old, alphas, u_first, n_ls, capped = self._host_line_search(
+            r["Ks"].astype(f64), r["ks"].astype(f64), x_nom.astype(f64), u_nom.astype(f64), lo.astype(f64), hi.astype(f64))
+        if capped.any():
+            warnings.warn("MPCstep line search hit the %d-trial cap on %d elements" % (MAX_LS_TRIALS, int(capped.sum())))
+        x, u = x.astype(dt), u.astype(dt)
+        assert not np.isnan(x).any() and not np.isnan(u).any()
+        self.back_out = LqrBackOut(n_total_qp_iter=int(r["n_qp"].max(axis=1).sum()))
+        self.for_out = LqrForOut(objs, scrambled_norm(u_nom - u_first, B, T, m), scrambled_norm(u_nom - u, B, T, m),
+                                 np.mean(alphas), costs)
+        self.aux = dict(Ks=r["Ks"], ks=r["ks"], alphas=alphas, free=r["free"], n_qp=r["n_qp"], n_ls=n_ls, old_costs=old,
+                        coupling=coupling, u_first=u_first, plugin=True)
         return x, u
 
     def forward(self, inputs):

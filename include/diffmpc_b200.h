@@ -168,6 +168,10 @@ int dmpc_pnqp(dmpc_handle h, int dtype, int B, int m,
  *   true dyn:   DMPC_DYN_LINEAR with d_tF[>=T-1,B,n,s], d_tf (nullable)  or
  *               DMPC_DYN_PENDULUM with h_dyn_params = {g, m, l, dt, max_torque} (env_dx/pendulum.py:31-102; dt and
  *               max_torque <= 0 mean the reference's 0.05 and 2.0); five doubles are read
+ * max_ls_trials: cap of the per-element line search (0: 64); < 0: backward_rec ONLY - the call writes d_Ks, d_ks, d_n_qp,
+ *   d_free and d_flags and returns, so that a host whose true cost / dynamics are Python callables (reference
+ *   mpc_step.py:237-251 calls them inside forward_rec) can run the line search itself; the true-cost / true-dynamics /
+ *   trajectory arguments may then be NULL.
  * Outputs: d_x[T,B,n] d_u[T,B,m]; gains d_Ks[T,B,m,n] d_ks[T,B,m]; d_u_first[T,B,m] = controls of the
  * alpha=1 pass (for full_du_norm, :260-263); d_objs[T,B]; d_costs[B]; d_old_costs[B] (nullable);
  * d_alphas[B]; d_n_qp[T,B] int32 (1 + PNQP iterations); d_free[T,B,m] uint8; d_n_ls[B] int32
