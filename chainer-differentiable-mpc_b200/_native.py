@@ -193,20 +193,27 @@ class PackedBuffers:
         self.base = DeviceArray(ctx, (self.total,), np.uint8)
         self.host = ctx.pinned_empty((self.total,), np.uint8)        # page-locked staging: copies run at PCIe speed
         self.views = {}
+        self.hviews = {}                                             # typed host views of the staging buffer, built once
         self._key = None
         for name, (off, shape, dt, nbytes) in self.layout.items():
             v = DeviceArray.__new__(DeviceArray)
             v.ctx, v.shape, v.dtype, v.nbytes, v.ptr, v._owned, v._base = ctx, shape, dt, nbytes, self.base.ptr + off, False, self.base
             self.views[name] = v
+            self.hviews[name] = self.host[off:off + nbytes].view(dt).reshape(shape)
 
     @classmethod
-    def acquire(cls, ctx, specs):
-        key = tuple((n, tuple(int(v) for v in sh), np.dtype(dt).str) for n, sh, dt in specs)
+    def acquire(cls, ctx, specs, key=None):
+        """`specs` = [(name, shape, dtype)] or a callable returning it (only evaluated on a cache miss); `key` = a cheap
+        hashable that identifies the layout (callers on a latency path pass one instead of having it derived per call)."""
+        if key is None:
+            if callable(specs):
+                specs = specs()
+            key = tuple((n, tuple(int(v) for v in sh), np.dtype(dt).str) for n, sh, dt in specs)
         cache = ctx.__dict__.setdefault("_packed_cache", {})
         lst = cache.get(key)
         if lst:
             return lst.pop()
-        pb = cls(ctx, specs)
+        pb = cls(ctx, specs() if callable(specs) else specs)
         pb._key = key
         return pb
 
@@ -216,20 +223,24 @@ class PackedBuffers:
         self.ctx.__dict__.setdefault("_packed_cache", {}).setdefault(self._key, []).append(self)
 
     def upload(self, arrays, stream=None):
-        host = self.host
+        hv = self.hviews
         for name, arr in arrays.items():
-            off, shape, dt, nbytes = self.layout[name]
-            a = np.asarray(arr)
-            assert a.shape == shape, (name, a.shape, shape)
-            host[off:off + nbytes].view(dt).reshape(shape)[...] = a
-        self.ctx._check(self.ctx.lib.dmpc_memcpy_h2d(self.ctx.h, self.base.ptr, host.ctypes.data, self.total, stream))
+            h = hv[name]
+            assert arr.shape == h.shape, (name, arr.shape, h.shape)
+            h[...] = arr
+        self.ctx._check(self.ctx.lib.dmpc_memcpy_h2d(self.ctx.h, self.base.ptr, self._host_ptr(), self.total, stream))
         return self.views
 
+    def _host_ptr(self):
+        p = self.__dict__.get("_hp")
+        if p is None:
+            p = self.__dict__["_hp"] = self.host.ctypes.data
+        return p
+
     def download(self, stream=None):
-        host = self.host
-        self.ctx._check(self.ctx.lib.dmpc_memcpy_d2h(self.ctx.h, host.ctypes.data, self.base.ptr, self.total, stream))
+        self.ctx._check(self.ctx.lib.dmpc_memcpy_d2h(self.ctx.h, self._host_ptr(), self.base.ptr, self.total, stream))
         self.ctx.sync(stream)
-        return {name: host[off:off + nbytes].view(dt).reshape(shape).copy() for name, (off, shape, dt, nbytes) in self.layout.items()}
+        return {name: h.copy() for name, h in self.hviews.items()}
 
     def free(self):
         self.base.free()

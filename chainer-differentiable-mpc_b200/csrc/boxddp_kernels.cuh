@@ -1,13 +1,15 @@
 // Device-side bookkeeping of the BoxDDP outer loop (reference mpc/box_ddp.py:121-230), so that an iLQR iteration
 // needs no host<->device traffic beyond one 32-byte status record:
-//   scrambled_norm_kernel : full_du_norm of mpc_step.py:261-263 - the reference's transpose(0,2,1).reshape(B, T*m)
+//   boxddp_norm_better_kernel : full_du_norm of mpc_step.py:261-263 - the reference's transpose(0,2,1).reshape(B, T*m)
 //                           mixes batch elements; that quirk is kept, and the row sums follow
-//                           numpy's pairwise summation so the values are the ones numpy would produce
-//   best_update_kernel    : per-element best trajectory (box_ddp.py:195-209) + the reductions the global exit
-//                           tests need (any improvement, max full_du_norm, OR of the per-element flags, NaN check)
+//                           numpy's pairwise summation so the values are the ones numpy would produce - plus the
+//                           per-element "better" test (box_ddp.py:195-209) and the reductions the global exit tests
+//                           need (any improvement, max full_du_norm, OR of the per-element flags, NaN check)
+//   boxddp_post_kernel    : best trajectory update, pendulum linearisation of the next nominal point, exit tests
 #pragma once
 #include <cuda_runtime.h>
 #include "common.cuh"
+#include "mpc_kernels.cuh"
 
 namespace dmpc {
 
@@ -48,8 +50,8 @@ __device__ R np_pairwise_sum(const Fn& f, int lo, int n) {
 }
 
 // Loop control that lives on the device, so that the host does not have to synchronise every iteration: after each
-// iteration boxddp_decide_kernel applies the reference's exit tests (box_ddp.py:184-230) to the reductions of
-// best_update_kernel and raises `done`; every kernel of a later iteration returns at once when it sees it.  The host
+// iteration the last CTA of boxddp_post_kernel applies the reference's exit tests (box_ddp.py:184-230) to the reductions
+// of boxddp_norm_better_kernel and raises `done`; every kernel of a later iteration returns at once when it sees it.  The host
 // enqueues a few iterations at a time and reads this record once per block.
 struct BoxDdpCtl {
   int done;              // 1 = an exit test fired (or a non-finite value was seen)
@@ -58,66 +60,58 @@ struct BoxDdpCtl {
   int n_not_improved;    // the reference's shared counter (box_ddp.py:184, 203, 226)
   int flags_or;          // OR of the per-element flags over all iterations
   int nonfinite;
-  int pad[2];
+  unsigned int ticket;   // CTAs of boxddp_post_kernel that have finished (the last one applies the exit tests)
+  int pad;
 };
 
-__global__ void boxddp_decide_kernel(BoxDdpStatus* st, BoxDdpCtl* ctl, int iter, double eps, int not_improved_lim) {
-  if (ctl->done) return;
+__device__ __forceinline__ void boxddp_decide(BoxDdpStatus* st, BoxDdpCtl* ctl, int iter, double eps, int not_improved_lim,
+                                              int nonfinite) {
   ctl->n_iter = iter + 1;
   ctl->flags_or |= st->flags_or;
   int nn = ctl->n_not_improved + 1;
   if (iter > 0 && st->any_better) nn = 0;
   ctl->n_not_improved = nn;
   const double max_du = __longlong_as_double((long long)st->max_du_bits);
-  if (st->nonfinite) { ctl->nonfinite = 1; ctl->done = 1; }
+  if (nonfinite) { ctl->nonfinite = 1; ctl->done = 1; }
   else if (max_du < eps) { ctl->status = DMPC_BOXDDP_CONVERGED; ctl->done = 1; }                 // box_ddp.py:223-225
   else if (nn > not_improved_lim) { ctl->status = DMPC_BOXDDP_NOT_IMPROVED; ctl->done = 1; }    // :227-229
   st->any_better = 0; st->flags_or = 0; st->nonfinite = 0; st->max_du_bits = 0ull;               // next iteration's reductions
 }
 
-// out[r] = sqrt(sum_q d[q]^2), q in [r L, (r+1) L), L = T m, where d is (a - b)[T,B,m] read in [T,m,B] order
+// ---- the two bookkeeping launches of a device-resident iteration ------------------------------------------------------
+// boxddp_norm_better_kernel (one thread per element): full_du_norm (scrambled, as above), the reference's per-element
+// "better" test and best-cost update (box_ddp.py:195-209) -> mask[b], and the batch-wide reductions of the exit tests.
 template <typename R>
-__global__ void scrambled_norm_kernel(int T, int B, int m, const R* a, const R* b, R* out, const int* skip) {
+__global__ void boxddp_norm_better_kernel(int T, int B, int m, int first, R best_cost_eps, const R* u_nom, const R* u_first,
+                                          const R* costs, const int* flags, R* du, R* bcosts, R* bdu, unsigned char* mask,
+                                          BoxDdpStatus* st, const int* skip) {
   if (skip && *skip) return;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= B) return;
-  const int L = T * m;
-  auto sq = [&](int q) -> R {
-    const long long qa = (long long)r * L + q;
-    const int bb = (int)(qa % B);
-    const int tj = (int)(qa / B);
-    const int t = tj / m, j = tj - t * m;
-    const size_t idx = ((size_t)t * B + bb) * m + j;
-    const R d = add_rn(a[idx], -b[idx]);
-    return mul_rn(d, d);
-  };
-  const R s = np_pairwise_sum<R>(sq, 0, L);
-  out[r] = sizeof(R) == 8 ? (R)sqrt((double)s) : (R)sqrtf((float)s);
-}
-
-template <typename R>
-__global__ void best_update_kernel(int T, int B, int n, int m, int first, R best_cost_eps, const R* x, const R* u,
-                                   const R* costs, const R* du, const int* flags, R* bx, R* bu, R* bcosts, R* bdu,
-                                   BoxDdpStatus* st, const int* skip) {
-  if (skip && *skip) return;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
   int better = 0, fl = 0, bad = 0;
   unsigned long long dub = 0ull;
-  if (b < B) {
-    const R cb = costs[b];
-    better = first ? 1 : (cb <= bcosts[b] + best_cost_eps);
-    fl = flags ? flags[b] : 0;
-    const R d = du[b];
+  if (r < B) {
+    const int L = T * m;
+    auto sq = [&](int q) -> R {
+      const long long qa = (long long)r * L + q;
+      const int bb = (int)(qa % B);
+      const int tj = (int)(qa / B);
+      const int t = tj / m, j = tj - t * m;
+      const size_t idx = ((size_t)t * B + bb) * m + j;
+      const R d = add_rn(u_nom[idx], -u_first[idx]);
+      return mul_rn(d, d);
+    };
+    const R ssum = np_pairwise_sum<R>(sq, 0, L);
+    const R d = sizeof(R) == 8 ? (R)sqrt((double)ssum) : (R)sqrtf((float)ssum);
+    du[r] = d;
+    const R cb = costs[r];
+    better = first ? 1 : (cb <= bcosts[r] + best_cost_eps);
+    fl = flags ? flags[r] : 0;
     bad = !(d == d) || !(cb == cb);
     dub = (unsigned long long)__double_as_longlong((double)d);
     if (d < R(0) || !(d == d)) dub = 0x7ff8000000000000ull;    // NaN sorts above every finite norm
-    for (int t = 0; t < T; ++t) {
-      for (int i = 0; i < n; ++i) { const R v = x[((size_t)t * B + b) * n + i]; bad |= !(v == v); if (better) bx[((size_t)t * B + b) * n + i] = v; }
-      for (int j = 0; j < m; ++j) { const R v = u[((size_t)t * B + b) * m + j]; bad |= !(v == v); if (better) bu[((size_t)t * B + b) * m + j] = v; }
-    }
-    if (better) { bcosts[b] = cb; bdu[b] = d; }
+    if (better) { bcosts[r] = cb; bdu[r] = d; }
+    mask[r] = (unsigned char)better;
   }
-  // warp-level reduction, then one atomic per warp
   const unsigned full = 0xffffffffu;
   better = __any_sync(full, better);
   bad = __any_sync(full, bad);
@@ -131,6 +125,44 @@ __global__ void best_update_kernel(int T, int B, int n, int m, int first, R best
     if (fl) atomicOr(&st->flags_or, fl);
     if (bad) atomicOr(&st->nonfinite, 1);
     atomicMax(&st->max_du_bits, dub);
+  }
+}
+
+// boxddp_post_kernel (one thread per (t, b)): best trajectory <- new trajectory where mask[b]; NaN check of the new
+// trajectory; pendulum: linearisation of the NEXT iteration's nominal point (x_new, u_new) - the step's accepted rollout
+// already is get_traj(u_new) (same pendulum_step, same inputs), so the per-iteration rollout launch of the reference loop
+// (box_ddp.py:123) reduces to this pointwise Jacobian; the last CTA to finish applies the exit tests.
+template <typename R>
+__global__ void boxddp_post_kernel(int T, int B, int n, int m, const R* x, const R* u, const unsigned char* mask, R* bx, R* bu,
+                                   const R* dyn_params, R* F_lin, BoxDdpStatus* st, BoxDdpCtl* ctl, int iter, double eps,
+                                   int not_improved_lim) {
+  if (ctl->done) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0;
+  if (i < (size_t)T * B) {
+    const int b = (int)(i % B);
+    const int t = (int)(i / B);
+    const bool better = mask[b] != 0;
+    for (int k = 0; k < n; ++k) { const R v = x[i * n + k]; bad |= !(v == v); if (better) bx[i * n + k] = v; }
+    for (int k = 0; k < m; ++k) { const R v = u[i * m + k]; bad |= !(v == v); if (better) bu[i * m + k] = v; }
+    if (F_lin && t < T - 1) {                                   // n = 3, m = 1 (checked by the C ABI)
+      R par[5], tau[4], xn[3], Fl[12];
+      for (int k = 0; k < 5; ++k) par[k] = dyn_params[k];
+      for (int k = 0; k < 3; ++k) { tau[k] = x[i * 3 + k]; xn[k] = x[(i + B) * 3 + k]; }
+      tau[3] = u[i];
+      pendulum_jacobian<R>(par, tau, xn, Fl, nullptr);
+      for (int k = 0; k < 12; ++k) F_lin[i * 12 + k] = Fl[k];
+    }
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(&st->nonfinite, 1);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      ctl->ticket = 0u;
+      const int nonfinite = atomicOr(&st->nonfinite, 0);      // through L2: the other CTAs' atomics of this launch
+      boxddp_decide(st, ctl, iter, eps, not_improved_lim, nonfinite);
+    }
   }
 }
 

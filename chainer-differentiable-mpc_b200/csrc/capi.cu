@@ -230,7 +230,7 @@ extern "C" int dmpc_get_traj(dmpc_handle, int, int, int, int, int, int, const vo
 // host reads one 32-byte status record to apply the reference's (batch-global) exit tests.
 namespace {
 struct BoxWs {
-  size_t x_nom, u_a, u_b, x_new, Ks, ks, u_first, objs, costs, old, alphas, du, n_qp, free_m, n_ls, flags, status, ctl, total;
+  size_t x_nom, u_a, u_b, x_new, Ks, ks, u_first, objs, costs, old, alphas, du, n_qp, free_m, n_ls, flags, mask, dynp, status, ctl, total;
 };
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 inline BoxWs box_ws(size_t w, int T, int B, int n, int m) {
@@ -240,7 +240,7 @@ inline BoxWs box_ws(size_t w, int T, int B, int n, int m) {
   L.Ks = take(w * T * B * m * n); L.ks = take(w * T * B * m); L.u_first = take(w * T * B * m); L.objs = take(w * T * B);
   L.costs = take(w * B); L.old = take(w * B); L.alphas = take(w * B); L.du = take(w * B);
   L.n_qp = take(sizeof(int) * (size_t)T * B); L.free_m = take((size_t)T * B * m); L.n_ls = take(sizeof(int) * (size_t)B);
-  L.flags = take(sizeof(int) * (size_t)B); L.status = take(sizeof(BoxDdpStatus)); L.ctl = take(sizeof(BoxDdpCtl));
+  L.flags = take(sizeof(int) * (size_t)B); L.mask = take((size_t)B); L.dynp = take(w * 5); L.status = take(sizeof(BoxDdpStatus)); L.ctl = take(sizeof(BoxDdpCtl));
   L.total = o;
   return L;
 }
@@ -265,30 +265,43 @@ static int boxddp_impl(dmpc_handle h, int dtype, int T, int B, int n, int m, con
   CK(cudaMemcpyAsync(u_cur, u_init, ub, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(dst, 0, sizeof(BoxDdpStatus), st));
   CK(cudaMemsetAsync(dctl, 0, sizeof(BoxDdpCtl), st));
-  // The loop runs on the device: the exit tests are boxddp_decide_kernel's, later iterations see ctl->done and return at
+  // The loop runs on the device: the exit tests run in the last CTA of boxddp_post_kernel, later iterations see ctl->done and return at
   // once, and the host only reads the control record once per block of `poll` enqueued iterations (no per-iteration sync).
   const int poll = o->poll_every > 0 ? o->poll_every : 8;
-  const int tpb = 128, grid = (B + tpb - 1) / tpb;
+  const int tpb = 64, grid = (B + tpb - 1) / tpb;                   // one thread per element: many small CTAs
+  const int ptpb = 128, pgrid = (int)(((size_t)T * B + ptpb - 1) / ptpb);   // one thread per (t, b)
+  unsigned char* mask = (unsigned char*)(w + L.mask);
+  R* d_dynp = (R*)(w + L.dynp);
+  if (pend) {
+    R hp[5];
+    for (int i = 0; i < 5; ++i) hp[i] = (R)dynp[i];
+    CK(cudaMemcpyAsync(d_dynp, hp, sizeof(hp), cudaMemcpyHostToDevice, st));   // pageable: staged before the call returns
+  }
   const int* skip = &dctl->done;
   BoxDdpCtl hc;
   memset(&hc, 0, sizeof(hc));
   for (int i0 = 0; i0 < o->max_iter && !hc.done; i0 += poll) {
     const int i1 = i0 + poll < o->max_iter ? i0 + poll : o->max_iter;
     for (int i = i0; i < i1; ++i) {
-      int rc = traj_impl<R>(h, T, B, n, m, dynamics, x_init, u_cur, F, f, dynp, x_nom, pend ? F_lin : nullptr,
-                            pend ? f_lin : nullptr, st, skip);
+      // nominal trajectory and linearisation (box_ddp.py:123-131).  Pendulum: after iteration 0 the step's accepted
+      // rollout x_new IS get_traj(u_new) and boxddp_post_kernel has linearised it, so no launch is needed here.
+      int rc = DMPC_OK;
+      if (!pend || i == 0)
+        rc = traj_impl<R>(h, T, B, n, m, dynamics, x_init, u_cur, F, f, dynp, x_nom, pend ? F_lin : nullptr,
+                          pend ? f_lin : nullptr, st, skip);
       if (rc) return rc;
       rc = mpc_forward_impl<R>(h, T, B, n, m, C, c, pend ? F_lin : F, pend ? T - 1 : F_T, nullptr, x_nom, u_cur, lo, hi, C, c,
                                dynamics, pend ? nullptr : F, pend ? nullptr : f, dynp, o->ls_decay, o->max_ls_trials, 1,
                                o->coupling, x_new, u_new, Ks, ks, u_first, objs, costs, old, alphas, n_qp, free_m, n_ls, flags,
                                st, skip);
       if (rc) return rc;
-      scrambled_norm_kernel<R><<<grid, tpb, 0, st>>>(T, B, m, u_cur, u_first, du, skip);
-      best_update_kernel<R><<<grid, tpb, 0, st>>>(T, B, n, m, i == 0, (R)o->best_cost_eps, x_new, u_new, costs, du, flags,
-                                                  (R*)x_best, (R*)u_best, (R*)costs_best, (R*)du_best, dst, skip);
-      boxddp_decide_kernel<<<1, 1, 0, st>>>(dst, dctl, i, o->eps, o->not_improved_lim);
-      h->launches += 3;
+      boxddp_norm_better_kernel<R><<<grid, tpb, 0, st>>>(T, B, m, i == 0, (R)o->best_cost_eps, u_cur, u_first, costs, flags, du,
+                                                         (R*)costs_best, (R*)du_best, mask, dst, skip);
+      boxddp_post_kernel<R><<<pgrid, ptpb, 0, st>>>(T, B, n, m, x_new, u_new, mask, (R*)x_best, (R*)u_best, d_dynp,
+                                                    pend ? (R*)F_lin : nullptr, dst, dctl, i, o->eps, o->not_improved_lim);
+      h->launches += 2;
       R* t_ = u_cur; u_cur = u_new; u_new = t_;                     // next nominal controls = this step's controls
+      if (pend) { t_ = x_nom; x_nom = x_new; x_new = t_; }          // ... and its rollout is the next nominal trajectory
     }
     CK(cudaMemcpyAsync(&hc, dctl, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -216,6 +216,7 @@ struct MpcFwdParams {
   unsigned char* free_mask;                                 // [T,B,m]
   int* n_ls; int* flags;                                    // [B]
   const int* skip;                                          // device flag (nullable): non-zero -> the launch is a no-op
+  int tpe_stash;                                            // mpc_forward_tpe_kernel: candidate-trajectory stash follows K|k in smem
 };
 
 // pendulum step (env_dx/pendulum.py:65-102, `simple` model); x=(cos,sin,dth), returns x'
@@ -228,10 +229,42 @@ __device__ __forceinline__ void pendulum_step(const R* par, const R* x, R u, R* 
   const R th = atan2(sth, cth);
   // same operation order as the reference expression, every op individually rounded (no FMA)
   const R t1 = mul_rn(mul_rn(R(-3.), g) / mul_rn(R(2.), l), -sth);
-  const R t2 = mul_rn(R(3.), uc) / mul_rn(mass, mul_rn(l, l));
+  const R u3 = mul_rn(R(3.), uc);
+  const R t2 = u3 == R(0) ? u3 : u3 / mul_rn(mass, mul_rn(l, l));   // (0 / x = 0 without the division's slow path)
   const R newdth = add_rn(dth, mul_rn(dt, add_rn(t1, t2)));
   const R newth = add_rn(th, mul_rn(newdth, dt));
   xn[0] = cos(newth); xn[1] = sin(newth); xn[2] = newdth;
+}
+
+// analytic Jacobian of the `simple` pendulum step at (x, u) given x' = pendulum_step(x, u): F = [R S] row-major [3][4] and
+// (nullable) f = x' - R x - S u, evaluated as (x' - R x) - S u like the reference (approximate.py:111-114).  Every
+// operation is individually rounded, so the linearisation does not depend on which kernel it was inlined into.
+template <typename R>
+__device__ __forceinline__ void pendulum_jacobian(const R* par, const R* tau, const R* xn, R* Fo, R* fo) {
+  const R g = par[0], mass = par[1], l = par[2];
+  const R dt = par[3] > R(0) ? par[3] : R(0.05), maxu = par[4] > R(0) ? par[4] : R(2.0);
+  const R c = tau[0], sn = tau[1], uraw = tau[3];
+  const R r2 = add_rn(mul_rn(c, c), mul_rn(sn, sn));
+  const R dth_dc = -sn / r2, dth_ds = c / r2;
+  const R a = mul_rn(R(3.), g) / mul_rn(R(2.), l), bu = R(3.) / mul_rn(mass, mul_rn(l, l));
+  const R inside = (uraw >= -maxu && uraw <= maxu) ? R(1) : R(0);
+  const R dnw[4] = {R(0), mul_rn(dt, a), R(1), mul_rn(mul_rn(dt, bu), inside)};
+  const R dnth[4] = {dth_dc, add_rn(dth_ds, mul_rn(dt, dnw[1])), dt, mul_rn(dt, dnw[3])};
+  const R cn = xn[0], snn = xn[1];
+  R J[3][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { J[0][j] = mul_rn(-snn, dnth[j]); J[1][j] = mul_rn(cn, dnth[j]); J[2][j] = dnw[j]; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Fo[i * 4 + j] = J[i][j];
+    if (fo) {
+      R rx = R(0);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) rx = fma_rn(J[i][j], tau[j], rx);
+      fo[i] = add_rn(add_rn(xn[i], -rx), -mul_rn(J[i][3], uraw));
+    }
+  }
 }
 
 struct MpcLayout {
@@ -590,27 +623,11 @@ __global__ void traj_kernel(TrajParams<R> p) {
     } else {
       pendulum_step(p.dyn_params, tau, tau[n], xn);
       if (p.Fout) {
-        // analytic Jacobian of the `simple` pendulum step; F = [R S], f = x' - R x - S u (approximate.py:111-114)
-        const R g = p.dyn_params[0], mass = p.dyn_params[1], l = p.dyn_params[2];
-        const R dt = p.dyn_params[3] > R(0) ? p.dyn_params[3] : R(0.05), maxu = p.dyn_params[4] > R(0) ? p.dyn_params[4] : R(2.0);
-        const R c = tau[0], sn = tau[1], uraw = tau[3];
-        const R r2 = c * c + sn * sn;
-        const R dth_dc = -sn / r2, dth_ds = c / r2;
-        const R a = R(3.) * g / (R(2.) * l), bu = R(3.) / (mass * (l * l));
-        const R inside = (uraw >= -maxu && uraw <= maxu) ? R(1) : R(0);
-        const R dnw[4] = {R(0), dt * a, R(1), dt * bu * inside};
-        const R dnth[4] = {dth_dc + dt * dnw[0], dth_ds + dt * dnw[1], dt * dnw[2], dt * dnw[3]};
-        const R cn = xn[0], snn = xn[1];
+        R Fl[12], fl[3];
+        pendulum_jacobian(p.dyn_params, tau, xn, Fl, fl);
         R* Fo = p.Fout + idx * 12; R* fo = p.fout + idx * 3;
-        R J[3][4];
-        for (int j = 0; j < 4; ++j) { J[0][j] = -snn * dnth[j]; J[1][j] = cn * dnth[j]; J[2][j] = dnw[j]; }
-        for (int i = 0; i < 3; ++i) {
-          // f = x' - R x - S u evaluated as (x' - R x) - S u like the reference
-          R rx = R(0);
-          for (int j = 0; j < 3; ++j) rx += J[i][j] * tau[j];
-          for (int j = 0; j < 4; ++j) Fo[i * 4 + j] = J[i][j];
-          fo[i] = (xn[i] - rx) - J[i][3] * uraw;
-        }
+        for (int i = 0; i < 12; ++i) Fo[i] = Fl[i];
+        for (int i = 0; i < 3; ++i) fo[i] = fl[i];
       }
     }
     for (int i = 0; i < n; ++i) tau[i] = xn[i];

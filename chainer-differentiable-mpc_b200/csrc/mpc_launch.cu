@@ -93,17 +93,22 @@ static int launch_elems(K kernel, const P& p, int G, size_t stride_bytes, int B,
 // m = 1, n <= 3: one thread per element, everything in registers (mpc_tpe_kernel.cuh).  DMPC_MPC_GROUP=1 selects the
 // group-per-element kernel for A/B runs.
 template <int N>
-static int launch_mpc_tpe(const MpcFwdParams<Rr>& p, bool batch, cudaStream_t st, long long* nl) {
+static int launch_mpc_tpe(const MpcFwdParams<Rr>& p_in, bool batch, cudaStream_t st, long long* nl) {
   // four candidate lanes per element (speculative parallel line search) while the K_t, k_t hand-over fits shared memory
-  // and - for batch coupling - the whole batch still fits one 256-thread CTA; otherwise one lane per element
-  const size_t kk = (size_t)p.T * (N + 1) * sizeof(Rr);            // bytes per element
-  static int spec = -1;
+  // and - for batch coupling - the whole batch still fits one 256-thread CTA; otherwise one lane per element.  When the
+  // candidate trajectories of lanes 1..3 fit too, they are stashed there (the winner copies instead of re-rolling).
+  MpcFwdParams<Rr> p = p_in;
+  const size_t kk = (size_t)tpe_kk_stride(p.T, N) * sizeof(Rr);            // bytes per element
+  const size_t ks = kk + 3 * (size_t)tpe_stash_stride(p.T, N) * sizeof(Rr);
+  static int spec = -1, stash_ok = -1;
   if (spec < 0) { const char* e = getenv("DMPC_MPC_NO_SPEC"); spec = (e && e[0] == '1') ? 0 : 1; }
+  if (stash_ok < 0) { const char* e = getenv("DMPC_MPC_NO_STASH"); stash_ok = (e && e[0] == '1') ? 0 : 1; }
   if (batch) {
     const int t4 = ((p.B * 4 + 31) / 32) * 32, t1 = ((p.B + 31) / 32) * 32;
     if (spec && t4 <= 256 && (t4 / 4) * kk <= (size_t)kMaxSmem) {
       auto k = mpc_forward_tpe_kernel<Rr, N, true, 256, 4>;
-      const size_t sm = (t4 / 4) * kk;
+      p.tpe_stash = (stash_ok && (t4 / 4) * ks <= (size_t)kMaxSmem) ? 1 : 0;
+      const size_t sm = (t4 / 4) * (p.tpe_stash ? ks : kk);
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA;
       k<<<1, t4, sm, st>>>(p);
     } else if (t1 <= 256) mpc_forward_tpe_kernel<Rr, N, true, 256, 1><<<1, t1, 0, st>>>(p);
@@ -119,7 +124,8 @@ static int launch_mpc_tpe(const MpcFwdParams<Rr>& p, bool batch, cudaStream_t st
     const int epb = 16;                                            // elements per CTA: many small CTAs spread over the SMs
     if (spec && epb * kk <= (size_t)kMaxSmem) {
       auto k = mpc_forward_tpe_kernel<Rr, N, false, 256, 4>;
-      const size_t sm = epb * kk;
+      p.tpe_stash = (stash_ok && epb * ks <= (size_t)kMaxSmem / 3) ? 1 : 0;      // keep three CTAs per SM resident
+      const size_t sm = epb * (p.tpe_stash ? ks : kk);
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA;
       k<<<(p.B + epb - 1) / epb, epb * 4, sm, st>>>(p);
     } else {

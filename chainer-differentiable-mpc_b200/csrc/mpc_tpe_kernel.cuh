@@ -27,8 +27,17 @@ __device__ __forceinline__ int pnqp_scalar(R H, R q, R lo, R hi, R& x, R* Hf_out
     const R g = q + H * x;
     act = ((x == lo) && (g > R(0))) || ((x == hi) && (g < R(0)));            // pnqp.py:110
     Hf = (act ? R(0) : H) + R(DMPC_PNQP_REG);
-    const R dx = (act ? R(0) : -g) / Hf;
-    const bool large = sqrt(dx * dx) >= R(DMPC_PNQP_TOL);                     // pnqp.py:139-140
+    // a zero numerator sends the compiler's double division down its slow path (~60 dependent instructions, taken by
+    // the whole warp); 0 / Hf is 0 (Hf = H + reg > 0 or the quotient's sign is irrelevant: only |dx| and x + alpha dx are used)
+    const R dx = (act || g == R(0)) ? R(0) : -g / Hf;
+    // pnqp.py:139-140 tests sqrt(dx^2) >= tol.  sqrt(dx*dx) is within 2 ulp of |dx|, so away from the threshold |dx| decides
+    // (same answer, no square root on the dependent chain); within ~50 ulp of it the literal expression is evaluated.
+    const R adx = fabs(dx);
+    constexpr double mg = sizeof(R) == 8 ? 1e-14 : 1e-5;
+    bool large;
+    if (adx >= R(DMPC_PNQP_TOL * (1.0 + mg))) large = true;
+    else if (adx <= R(DMPC_PNQP_TOL * (1.0 - mg))) large = false;
+    else large = sqrt(dx * dx) >= R(DMPC_PNQP_TOL);
     bool any_large = large;
     if (BATCH) any_large = batch_or(large ? 1 : 0, bphase) != 0;
     if (!any_large) break;                                                    // x is returned before dx is applied (Q4)
@@ -57,6 +66,62 @@ __device__ __forceinline__ int pnqp_scalar(R H, R q, R lo, R hi, R& x, R* Hf_out
   return it;
 }
 
+// Operands of one Riccati step / one rollout step, loaded at the top of the step.  (Requesting step t-1's operands before
+// step t is computed - a register double buffer - was measured and is slower: 255 registers + spills, 96-101 us against
+// 90 us on the batch-64 step, profiles/r2/tpe_variants_ab.txt.)
+template <typename R, int N>
+struct TpeSweepOps {
+  R C[N + 1][N + 1], c[N + 1], tau[N + 1], lo, hi, F[N][N + 1], f[N];
+};
+template <typename R, int N>
+struct TpeRollOps {
+  R xn[N], un, lo, hi, C[(N + 1) * (N + 1)], c[N + 1];
+};
+
+template <typename R, int N>
+__device__ __forceinline__ void tpe_load_sweep(const MpcFwdParams<R>& p, int t, int e, bool have_f, TpeSweepOps<R, N>& o) {
+  constexpr int n = N, s = N + 1;
+  const size_t idx = (size_t)t * p.B + e;
+  const R* Cg = p.C + idx * s * s; const R* cg = p.c + idx * s;
+#pragma unroll
+  for (int i = 0; i < s; ++i) {
+#pragma unroll
+    for (int j = 0; j < s; ++j) o.C[i][j] = Cg[i * s + j];
+    o.c[i] = cg[i];
+  }
+#pragma unroll
+  for (int i = 0; i < n; ++i) o.tau[i] = p.x_nom[idx * n + i];
+  o.tau[n] = p.u_nom[idx];
+  o.lo = p.lo[idx]; o.hi = p.hi[idx];
+  if (t < p.T - 1) {
+    const R* Fg = p.F + idx * n * s;
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+      for (int j = 0; j < s; ++j) o.F[i][j] = Fg[i * s + j];
+#pragma unroll
+    for (int i = 0; i < n; ++i) o.f[i] = have_f ? p.f[idx * n + i] : R(0);
+  }
+}
+
+template <typename R, int N>
+__device__ __forceinline__ void tpe_load_roll(const MpcFwdParams<R>& p, int t, int e, TpeRollOps<R, N>& o) {
+  constexpr int n = N, s = N + 1;
+  const size_t idx = (size_t)t * p.B + e;
+#pragma unroll
+  for (int i = 0; i < n; ++i) o.xn[i] = p.x_nom[idx * n + i];
+  o.un = p.u_nom[idx]; o.lo = p.lo[idx]; o.hi = p.hi[idx];
+  const R* Cg = p.tC + idx * s * s; const R* cg = p.tc + idx * s;
+#pragma unroll
+  for (int i = 0; i < s * s; ++i) o.C[i] = Cg[i];
+#pragma unroll
+  for (int i = 0; i < s; ++i) o.c[i] = cg[i];
+}
+
+// shared-memory strides (in elements), odd so that the lanes of a warp fall into different banks
+__host__ __device__ inline int tpe_kk_stride(int T, int n) { return (T * (n + 1)) | 1; }        // K_t | k_t per element
+__host__ __device__ inline int tpe_stash_stride(int T, int n) { return (T * (n + 2)) | 1; }     // x_t | u_t | obj_t per lane
+
 // MAXT = largest CTA the instantiation is launched with (register budget: 256 threads leave 255 registers per thread).
 // NA   = lanes per element.  NA = 1: plain thread-per-element.  NA = 4: SPECULATIVE PARALLEL LINE SEARCH - the four
 //        adjacent lanes of an element run the Riccati sweep redundantly (same registers, no communication) and then roll
@@ -64,6 +129,8 @@ __device__ __forceinline__ int pnqp_scalar(R H, R q, R lo, R hi, R& x, R* Hf_out
 //        the reference's order) whose cost does not exceed the old cost wins (mpc_step.py:196, Q5).  The reference
 //        evaluates the candidates one after the other; each one is independent of the previous ones, so the selected
 //        alpha and trajectory are the same - the dependent chain is one horizon pass instead of (1 + trials) passes.
+//        Lane 0 writes its candidate straight to x, u, objs; lanes 1..3 keep theirs in shared memory (p.tpe_stash) and the
+//        winner copies it out - without the stash the winner rolls the horizon a second time.
 template <typename R, int N, bool BATCH, int MAXT, int NA>
 __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p) {
   static_assert(NA == 1 || NA == 4, "lanes per element");
@@ -83,7 +150,10 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
   int status = 0;
   unsigned bphase = 0;                                      // batch_or flag slot (BATCH coupling over a cluster)
   // NA > 1: K_t, k_t of the element are handed from the sweep to its candidate lanes through shared memory
-  R* Kk = reinterpret_cast<R*>(smem_raw) + (size_t)(threadIdx.x / NA) * T * (n + 1);
+  R* Kk = reinterpret_cast<R*>(smem_raw) + (size_t)(threadIdx.x / NA) * tpe_kk_stride(T, n);
+  const bool use_stash = NA > 1 && p.tpe_stash != 0;
+  R* stash = reinterpret_cast<R*>(smem_raw) + (size_t)(blockDim.x / NA) * tpe_kk_stride(T, n) +
+             (size_t)((threadIdx.x / NA) * (NA - 1) + (a > 0 ? a - 1 : 0)) * tpe_stash_stride(T, n);
 
   // =========================== backward_rec (mpc_step.py:70-173) ===========================
   {
@@ -91,28 +161,17 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
     R kprev = R(0);
     for (int t = T - 1; t >= 0; --t) {
       const size_t idx = (size_t)t * tb + e;
-      R C[s][s], c[s], tau[s];
-      {
-        const R* Cg = p.C + idx * s * s; const R* cg = p.c + idx * s;
-#pragma unroll
-        for (int i = 0; i < s; ++i) {
-#pragma unroll
-          for (int j = 0; j < s; ++j) C[i][j] = Cg[i * s + j];
-          c[i] = cg[i];
-        }
-#pragma unroll
-        for (int i = 0; i < n; ++i) tau[i] = p.x_nom[idx * n + i];
-        tau[n] = p.u_nom[idx];
-      }
-      const R lb = p.lo[idx] - tau[n], ub = p.hi[idx] - tau[n];               // :136-138
+      TpeSweepOps<R, N> cur;
+      tpe_load_sweep<R, N>(p, t, e, have_f, cur);
+      const R lb = cur.lo - cur.tau[n], ub = cur.hi - cur.tau[n];             // :136-138
       if (lb > ub) status |= FLAG_BAD_BOUNDS;                                  // the reference asserts (:139)
       R Q[s][s], q[s];
 #pragma unroll
       for (int o = 0; o < s; ++o) {                                            // Taylor shift c_hat = C tau + c (:305-316)
-        R acc = c[o];
+        R acc = cur.c[o];
         if (expand) {
 #pragma unroll
-          for (int j = 0; j < s; ++j) acc += C[o][j] * tau[j];
+          for (int j = 0; j < s; ++j) acc += cur.C[o][j] * cur.tau[j];
         }
         q[o] = acc;
       }
@@ -120,27 +179,22 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
 #pragma unroll
         for (int i = 0; i < s; ++i)
 #pragma unroll
-          for (int j = 0; j < s; ++j) Q[i][j] = C[i][j];
+          for (int j = 0; j < s; ++j) Q[i][j] = cur.C[i][j];
       } else {
-        R F[n][s], Mx[n][s], mv[n];
-        const R* Fg = p.F + idx * n * s;
-#pragma unroll
-        for (int i = 0; i < n; ++i)
-#pragma unroll
-          for (int j = 0; j < s; ++j) F[i][j] = Fg[i * s + j];
+        R Mx[n][s], mv[n];
 #pragma unroll
         for (int i = 0; i < n; ++i) {                                          // Mx = V F ; mv = V f + v
 #pragma unroll
           for (int j = 0; j < s; ++j) {
             R acc = R(0);
 #pragma unroll
-            for (int k = 0; k < n; ++k) acc += V[i][k] * F[k][j];
+            for (int k = 0; k < n; ++k) acc += V[i][k] * cur.F[k][j];
             Mx[i][j] = acc;
           }
           R acc = v[i];
           if (have_f) {
 #pragma unroll
-            for (int k = 0; k < n; ++k) acc += V[i][k] * p.f[idx * n + k];
+            for (int k = 0; k < n; ++k) acc += V[i][k] * cur.f[k];
           }
           mv[i] = acc;
         }
@@ -148,13 +202,13 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
         for (int i = 0; i < s; ++i) {                                          // Q = C + F^T Mx ; q = c_hat + F^T mv
 #pragma unroll
           for (int j = 0; j < s; ++j) {
-            R acc = C[i][j];
+            R acc = cur.C[i][j];
 #pragma unroll
-            for (int k = 0; k < n; ++k) acc += F[k][i] * Mx[k][j];
+            for (int k = 0; k < n; ++k) acc += cur.F[k][i] * Mx[k][j];
             Q[i][j] = acc;
           }
 #pragma unroll
-          for (int k = 0; k < n; ++k) q[i] += F[k][i] * mv[k];
+          for (int k = 0; k < n; ++k) q[i] += cur.F[k][i] * mv[k];
         }
       }
       // ---- PNQP on (Quu, qu, lb, ub), warm start k_{t+1} (:141-146)
@@ -165,7 +219,8 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
       const int it = pnqp_scalar<BATCH>(Huu, quu, lb, ub, kprev, &Hf, &is_free, p.n_qp_iter, &status, bphase);
       R K[n], P[s];
 #pragma unroll
-      for (int j = 0; j < n; ++j) K[j] = (is_free ? -Q[n][j] : R(0)) / Hf;    // rows of clamped controls zeroed (:147-157)
+      for (int j = 0; j < n; ++j)                                              // rows of clamped controls zeroed (:147-157)
+        K[j] = (is_free && Q[n][j] != R(0)) ? -Q[n][j] / Hf : R(0);            // (0 / Hf without the division's slow path)
 #pragma unroll
       for (int j = 0; j < n; ++j) P[j] = Q[n][j] + Huu * K[j];                // P = [Qux | qu] + Quu [K | k]  (unmasked, Q6)
       P[n] = quu + Huu * kprev;
@@ -201,26 +256,34 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
 
   // =========================== forward_rec (mpc_step.py:175-286) ===========================
   // One horizon pass evaluates the cost of the nominal trajectory (xpget_cost, :191) AND the candidate alpha of this
-  // lane; `write` makes the pass store its trajectory (candidate 0 of round 0 always does: it also is u_first).
+  // lane.  mode 0: evaluate only; 1: write x, u, objs (+ u_first on the first pass); 2: keep x, u, objs in the stash.
   const bool linear = p.dynamics == DMPC_DYN_LINEAR;
   R old_cost = R(0), cost = R(0), alpha = R(1);
-  auto rollout = [&](R al, bool write, bool first) {
+  auto rollout = [&](R al, int mode, bool first) {
     R oc = R(0), cc = R(0);
     R xnew[n];
     for (int t = 0; t < T; ++t) {
       const size_t idx = (size_t)t * tb + e;
-      R tau[s], xn[n], tn[s];
+      TpeRollOps<R, N> cur;
+      tpe_load_roll<R, N>(p, t, e, cur);
+      R Fr[n][s], fr[n];
+      if (linear && t < T - 1) {                                               // true dynamics of this step, requested early
 #pragma unroll
-      for (int i = 0; i < n; ++i) xn[i] = p.x_nom[idx * n + i];
-      const R un = p.u_nom[idx];
+        for (int o = 0; o < n; ++o) {
+#pragma unroll
+          for (int j = 0; j < s; ++j) Fr[o][j] = p.tF[idx * n * s + o * s + j];
+          fr[o] = p.tf ? p.tf[idx * n + o] : R(0);
+        }
+      }
+      R tau[s], tn[s];
       R dxv[n];
 #pragma unroll
       for (int i = 0; i < n; ++i) {
-        if (t == 0) xnew[i] = xn[i];                                           // new_x[0] = states[0]
-        tau[i] = xnew[i]; tn[i] = xn[i];
-        dxv[i] = (t == 0) ? R(0) : xnew[i] - xn[i];
+        if (t == 0) xnew[i] = cur.xn[i];                                       // new_x[0] = states[0]
+        tau[i] = xnew[i]; tn[i] = cur.xn[i];
+        dxv[i] = (t == 0) ? R(0) : xnew[i] - cur.xn[i];
       }
-      tn[n] = un;
+      tn[n] = cur.un;
       R Kt[n], kt;
       if (NA > 1) {
 #pragma unroll
@@ -231,40 +294,38 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
         for (int i = 0; i < n; ++i) Kt[i] = p.Ks[idx * n + i];
         kt = p.ks[idx];
       }
-      R nu = dot2(Kt, 1, dxv, n, R(0)) + un;                                   // :209
+      R nu = dot2(Kt, 1, dxv, n, R(0)) + cur.un;                               // :209
       nu += al * kt;                                                           // :213-219
-      nu = fmin(fmax(nu, p.lo[idx]), p.hi[idx]);                               // :221
+      nu = fmin(fmax(nu, cur.lo), cur.hi);                                     // :221
       tau[n] = nu;
       // objectives 0.5 (tau^T C) tau + tau . c   (:251) of the candidate and (first pass) of the nominal trajectory
-      const R* Cg = p.tC + idx * s * s; const R* cg = p.tc + idx * s;
       R quad = R(0), lin = R(0), quad0 = R(0), lin0 = R(0);
 #pragma unroll
       for (int j = 0; j < s; ++j) {
         R tj = R(0), tj0 = R(0);
 #pragma unroll
-        for (int i = 0; i < s; ++i) { const R cij = Cg[i * s + j]; tj += tau[i] * cij; tj0 += tn[i] * cij; }
+        for (int i = 0; i < s; ++i) { const R cij = cur.C[i * s + j]; tj += tau[i] * cij; tj0 += tn[i] * cij; }
         quad += tj * tau[j]; quad0 += tj0 * tn[j];
-        lin += tau[j] * cg[j]; lin0 += tn[j] * cg[j];
+        lin += tau[j] * cur.c[j]; lin0 += tn[j] * cur.c[j];
       }
       const R obj = R(0.5) * quad + lin;
       cc += obj;
       if (first) oc += R(0.5) * quad0 + lin0;
-      if (write) {
+      if (mode == 1) {
 #pragma unroll
         for (int i = 0; i < n; ++i) p.x[idx * n + i] = tau[i];
         p.u[idx] = tau[n];
         if (first && p.u_first) p.u_first[idx] = tau[n];
         if (p.objs) p.objs[idx] = obj;
+      } else if (mode == 2) {
+#pragma unroll
+        for (int i = 0; i < s; ++i) stash[t * (n + 2) + i] = tau[i];
+        stash[t * (n + 2) + s] = obj;
       }
       if (t < T - 1) {
         if (linear) {
-          R Fr[s];
 #pragma unroll
-          for (int o = 0; o < n; ++o) {
-#pragma unroll
-            for (int j = 0; j < s; ++j) Fr[j] = p.tF[idx * n * s + o * s + j];
-            xnew[o] = dot2(Fr, 1, tau, s, p.tf ? p.tf[idx * n + o] : R(0));
-          }
+          for (int o = 0; o < n; ++o) xnew[o] = dot2(Fr[o], 1, tau, s, fr[o]);
         } else {
           if constexpr (N == 3) {
             R nx[3];
@@ -282,7 +343,7 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
   if (NA == 1) {
     bool done = false;
     while (!done) {
-      rollout(alpha, valid, trial == 0);
+      rollout(alpha, valid ? 1 : 0, trial == 0);
       const bool worse = cost > old_cost;                   // NaN -> accepted, as in the reference
       if (!worse) done = true;
       else if (trial + 1 >= p.max_ls_trials) { status |= FLAG_LS_CAPPED; done = true; }   // alpha = the one written
@@ -301,7 +362,9 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
       R al = R(1);
       for (int i = 0; i < k; ++i) al *= p.ls_decay;         // the reference's repeated multiplication (bit-identical)
       const bool in_range = k < p.max_ls_trials;
-      if (open && in_range) rollout(al, writer && round == 0, round == 0);
+      // lane 0 writes its candidate in place (round 0: it also is u_first); a later winner overwrites it
+      const int mode = (a == 0) ? (valid ? 1 : 0) : (use_stash ? 2 : 0);
+      if (open && in_range) rollout(al, mode, round == 0);
       if (round == 0) old_cost = __shfl_sync(full, old_cost, qbase);            // every lane computed the same value
       const bool ok = open && in_range && !(cost > old_cost);                   // NaN -> accepted, as in the reference
       const unsigned bal = (__ballot_sync(full, ok) >> qbase) & ((1u << NA) - 1u);
@@ -315,7 +378,19 @@ __global__ void __launch_bounds__(MAXT) mpc_forward_tpe_kernel(MpcFwdParams<R> p
         win = NA * round + wa;
         wcost = c_w; walpha = a_w;
         if (capped) status |= FLAG_LS_CAPPED;
-        if (win != 0 && a == wa && valid) rollout(al, true, false);            // a later candidate won: write its trajectory
+        if (wa != 0 && a == wa && valid) {                  // a stashing lane won: its trajectory goes out
+          if (use_stash) {
+            for (int t = 0; t < T; ++t) {
+              const size_t idx = (size_t)t * tb + e;
+#pragma unroll
+              for (int i = 0; i < n; ++i) p.x[idx * n + i] = stash[t * (n + 2) + i];
+              p.u[idx] = stash[t * (n + 2) + n];
+              if (p.objs) p.objs[idx] = stash[t * (n + 2) + s];
+            }
+          } else {
+            rollout(al, 1, false);
+          }
+        }
       }
     }
     trial = win + ((status & FLAG_LS_CAPPED) ? 1 : 0);

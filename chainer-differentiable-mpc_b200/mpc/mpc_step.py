@@ -155,19 +155,22 @@ class MPCstep(FunctionNodeBase):
         else:
             dyn, params = _native.DYN_PENDULUM, pendulum_params(self.true_dynamics)
             tf = None
-        out_specs = [("x", (T, B, n), dt), ("u", (T, B, m), dt), ("Ks", (T, B, m, n), dt), ("ks", (T, B, m), dt),
-                     ("u_first", (T, B, m), dt), ("objs", (T, B), dt), ("costs", (B,), dt), ("old", (B,), dt),
-                     ("alphas", (B,), dt), ("n_qp", (T, B), np.int32), ("free", (T, B, m), np.uint8),
-                     ("n_ls", (B,), np.int32), ("flags", (B,), np.int32)]
+        def out_specs():
+            return [("x", (T, B, n), dt), ("u", (T, B, m), dt), ("Ks", (T, B, m, n), dt), ("ks", (T, B, m), dt),
+                    ("u_first", (T, B, m), dt), ("objs", (T, B), dt), ("costs", (B,), dt), ("old", (B,), dt),
+                    ("alphas", (B,), dt), ("n_qp", (T, B), np.int32), ("free", (T, B, m), np.uint8),
+                    ("n_ls", (B,), np.int32), ("flags", (B,), np.int32)]
         packed = sum(a.nbytes for a in ins.values()) <= _native.PACK_LIMIT_BYTES
         if packed:
-            pin = _native.PackedBuffers.acquire(ctx, [(k, a.shape, dt) for k, a in ins.items()])
+            lkey = (T, B, n, m, dt.char, F_hat.shape[0])
+            pin = _native.PackedBuffers.acquire(ctx, lambda: [(k, a.shape, dt) for k, a in ins.items()],
+                                                key=("mpc_in", tuple((k, a.shape[0]) for k, a in ins.items())) + lkey)
             d = pin.upload(ins)
-            pout = _native.PackedBuffers.acquire(ctx, out_specs)
+            pout = _native.PackedBuffers.acquire(ctx, lambda: out_specs(), key=("mpc_out",) + lkey)
             o = pout.views
         else:
             d = {k: ctx.to_device(a) for k, a in ins.items()}
-            o = {k: ctx.empty(shape, t) for k, shape, t in out_specs}
+            o = {k: ctx.empty(shape, t) for k, shape, t in out_specs()}
         dtC, dtc = d.get("tC", d["C"]), d.get("tc", d["c"])
         dtF = d.get("tF", d["F"]) if dyn == _native.DYN_LINEAR else None
         dtf = d.get("tf") if dyn == _native.DYN_LINEAR else None

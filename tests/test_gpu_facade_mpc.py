@@ -168,7 +168,7 @@ def test_boxddp_device_loop_equals_host_loop(case, capsys):
 
 
 def test_boxddp_device_loop_scrambled_norm_long_rows():
-    """T*m > 128 exercises the recursive branch of numpy's pairwise summation in scrambled_norm_kernel."""
+    """T*m > 128 exercises the recursive branch of numpy's pairwise summation in boxddp_norm_better_kernel."""
     from box_ddp import BoxDDP
     from util import QuadCost, LinDx
     rs = np.random.RandomState(5)

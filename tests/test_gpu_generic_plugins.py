@@ -107,18 +107,23 @@ def _pendulum_problem(B, T=20, seed=0):
     return x0, C, c, q, p
 
 
-def test_boxddp_with_an_opaque_pendulum_callable_and_callable_cost():
+def test_boxddp_with_an_opaque_pendulum_callable_and_callable_cost(monkeypatch):
     """The pendulum handed over as a plain Python function and the quadratic cost as a callable: BoxDDP linearises /
-    approximates on the host (finite differences), sweeps on the GPU, line-searches on the host, and lands on the solution
-    of the fused device loop; the adjoint of the final no-op step agrees too."""
+    approximates on the host (finite differences), sweeps on the GPU, line-searches on the host, and follows the fused
+    device loop iteration for iteration (fixed number of iterations: the comparison must not depend on where a hard
+    swing-up instance stops); the adjoint of the final no-op step agrees too."""
     from box_ddp import BoxDDP
     from pendulum_dx import PendulumDx
     from util import QuadCost
     from oracle import pendulum as pend
-    B, T = 24, 20
+    # the pendulum clips its torque at +-2 = the control bounds: inside the feasible set the clip never acts, but it puts a
+    # kink exactly where clamped controls sit and a central difference there returns half the slope (the analytic
+    # linearisation and Chainer's F.clip take the inclusive one, SURVEY H3).  The callable under test is the smooth map.
+    monkeypatch.setattr(pend, "MAX_TORQUE", 1e9)
+    B, T = 12, 20
     x0, C, c, q, p = _pendulum_problem(B, T)
-    kw = dict(T=T, u_lower=-2.0, u_upper=2.0, n_batch=B, n_state=3, n_ctrl=1, u_init=None, eps=1e-3, max_iter=60,
-              line_search_decay=0.2, max_line_search_iter=5, update_dynamics=True)
+    kw = dict(T=T, u_lower=-2.0, u_upper=2.0, n_batch=B, n_state=3, n_ctrl=1, u_init=None, eps=1e-9, max_iter=4,
+              line_search_decay=0.2, max_line_search_iter=5, update_dynamics=True, exit_unconverged=False)
     sink = io.StringIO()
     with contextlib.redirect_stdout(sink), warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -127,17 +132,17 @@ def test_boxddp_with_an_opaque_pendulum_callable_and_callable_cost():
         plug = BoxDDP(**kw)
         xp_, up_, cp_ = plug((x0, lambda tau: 0.5 * (arr(tau) ** 2) @ q + arr(tau) @ p,
                               lambda x, u: pend.step(arr(x), arr(u))))
-    assert plug.info["status"] == fused.info["status"] == "converged"
-    # same fixed point up to the finite-difference derivatives (~1e-7 in the Hessian) amplified by the iLQR iterations
-    assert np.abs(arr(up_) - arr(uf)).max() < 5e-3 and np.abs(arr(xp_) - arr(xf)).max() < 5e-3
-    assert np.abs(cp_ - cf).max() < 1e-4 * np.abs(cf).max()
+    assert plug.info["n_iter"] == fused.info["n_iter"] == 4
+    # finite-difference derivatives (~1e-7 relative in the Hessian) through four iLQR iterations
+    assert np.abs(arr(up_) - arr(uf)).max() < 1e-4 and np.abs(arr(xp_) - arr(xf)).max() < 1e-4
+    assert np.abs(cp_ - cf).max() < 1e-5 * np.abs(cf).max()
     # gradient path: the final no-op MPCstep carries finite-difference C, c, F, f of the callables
     gu = np.random.RandomState(1).randn(T, B, 1)
     gf = fused.last_step.backward_numpy(None, gu)
     gp = plug.last_step.backward_numpy(None, gu)
     for a, b, k in zip(gp, gf, ("dx0", "dC", "dc", "dF", "df")):
         assert np.isfinite(a).all(), k
-        assert np.abs(a - b).max() < 2e-2 * max(np.abs(b).max(), 1e-3), k
+        assert np.abs(a - b).max() < 1e-3 * max(np.abs(b).max(), 1e-3), k
 
 
 def test_boxddp_linear_callable_matches_lindx():

@@ -1,4 +1,4 @@
-"""CPU: the summation order that scrambled_norm_kernel (csrc/boxddp_kernels.cuh) implements is numpy's pairwise
+"""CPU: the summation order that boxddp_norm_better_kernel (csrc/boxddp_kernels.cuh) implements is numpy's pairwise
 summation of a contiguous float64 row (numpy/core/src/umath/loops_utils.h.src).  The device-resident BoxDDP loop is
 bit-identical to the host loop only while this holds, so the restatement is pinned against the installed numpy."""
 import numpy as np
@@ -42,7 +42,7 @@ def test_row_sum_of_squares_matches_numpy_bit_for_bit(n):
 def test_scrambled_reshape_indexing():
     """Row r of transpose(du,(0,2,1)).reshape(B, T*m) (reference mpc_step.py:261-263) holds the flat elements
     q = r*T*m .. (r+1)*T*m - 1 of the [T,m,B]-ordered array: (t, j, b) = (q // (m*B), (q // B) % m, q % B) - the
-    index arithmetic of scrambled_norm_kernel."""
+    index arithmetic of boxddp_norm_better_kernel."""
     T, B, m = 5, 7, 3
     du = np.arange(T * B * m, dtype=np.float64).reshape(T, B, m)
     d = np.transpose(du, (0, 2, 1)).reshape(B, T * m)
