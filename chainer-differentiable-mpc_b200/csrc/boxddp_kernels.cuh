@@ -132,8 +132,10 @@ __global__ void boxddp_norm_better_kernel(int T, int B, int m, int first, R best
 // trajectory; pendulum: linearisation of the NEXT iteration's nominal point (x_new, u_new) - the step's accepted rollout
 // already is get_traj(u_new) (same pendulum_step, same inputs), so the per-iteration rollout launch of the reference loop
 // (box_ddp.py:123) reduces to this pointwise Jacobian; the last CTA to finish applies the exit tests.
+constexpr int kPostThreads = 128;
+
 template <typename R>
-__global__ void boxddp_post_kernel(int T, int B, int n, int m, const R* x, const R* u, const unsigned char* mask, R* bx, R* bu,
+__global__ void __launch_bounds__(kPostThreads) boxddp_post_kernel(int T, int B, int n, int m, const R* x, const R* u, const unsigned char* mask, R* bx, R* bu,
                                    const R* dyn_params, R* F_lin, BoxDdpStatus* st, BoxDdpCtl* ctl, int iter, double eps,
                                    int not_improved_lim) {
   if (ctl->done) return;
@@ -145,13 +147,34 @@ __global__ void boxddp_post_kernel(int T, int B, int n, int m, const R* x, const
     const bool better = mask[b] != 0;
     for (int k = 0; k < n; ++k) { const R v = x[i * n + k]; bad |= !(v == v); if (better) bx[i * n + k] = v; }
     for (int k = 0; k < m; ++k) { const R v = u[i * m + k]; bad |= !(v == v); if (better) bu[i * m + k] = v; }
-    if (F_lin && t < T - 1) {                                   // n = 3, m = 1 (checked by the C ABI)
-      R par[5], tau[4], xn[3], Fl[12];
-      for (int k = 0; k < 5; ++k) par[k] = dyn_params[k];
-      for (int k = 0; k < 3; ++k) { tau[k] = x[i * 3 + k]; xn[k] = x[(i + B) * 3 + k]; }
-      tau[3] = u[i];
-      pendulum_jacobian<R>(par, tau, xn, Fl, nullptr);
-      for (int k = 0; k < 12; ++k) F_lin[i * 12 + k] = Fl[k];
+  }
+  // pendulum (n = 3, m = 1, checked by the C ABI): Jacobian rows of this CTA's (t, b) range are staged in shared memory and
+  // written as one contiguous run (a thread's own 12 doubles are 96 bytes apart from its neighbour's: storing them
+  // directly costs four partial-sector writes per sector)
+  if (F_lin) {
+    __shared__ R sF[kPostThreads * 13];                        // row stride 13: conflict-free staging writes
+    const size_t total = (size_t)T * B;
+    if (i < total) {
+      const int t = (int)(i / B);
+      R Fl[12];
+      if (t < T - 1) {
+        R par[5], tau[4], xn[3];
+        for (int k = 0; k < 5; ++k) par[k] = dyn_params[k];
+        for (int k = 0; k < 3; ++k) { tau[k] = x[i * 3 + k]; xn[k] = x[(i + B) * 3 + k]; }
+        tau[3] = u[i];
+        pendulum_jacobian<R>(par, tau, xn, Fl, nullptr);
+      } else {
+        for (int k = 0; k < 12; ++k) Fl[k] = R(0);
+      }
+      for (int k = 0; k < 12; ++k) sF[threadIdx.x * 13 + k] = Fl[k];
+    }
+    __syncthreads();
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x;
+    const size_t lim = (size_t)(T - 1) * B;                      // F_lin has T-1 time rows
+    const size_t i1 = i0 + blockDim.x < lim ? i0 + blockDim.x : lim;
+    if (i1 > i0) {
+      const int cnt = (int)(i1 - i0) * 12;
+      for (int k = threadIdx.x; k < cnt; k += blockDim.x) F_lin[i0 * 12 + k] = sF[(k / 12) * 13 + k % 12];
     }
   }
   if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(&st->nonfinite, 1);

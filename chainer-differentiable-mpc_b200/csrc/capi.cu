@@ -13,6 +13,8 @@ struct dmpc_ctx {
   cudaStream_t stream = nullptr;
   long long launches = 0;
   std::string err;
+  void* pinned = nullptr;        // small page-locked scratch (BoxDDP control records), allocated on first use
+  cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 
 using namespace dmpc;
@@ -269,7 +271,7 @@ static int boxddp_impl(dmpc_handle h, int dtype, int T, int B, int n, int m, con
   // once, and the host only reads the control record once per block of `poll` enqueued iterations (no per-iteration sync).
   const int poll = o->poll_every > 0 ? o->poll_every : 8;
   const int tpb = 64, grid = (B + tpb - 1) / tpb;                   // one thread per element: many small CTAs
-  const int ptpb = 128, pgrid = (int)(((size_t)T * B + ptpb - 1) / ptpb);   // one thread per (t, b)
+  const int pgrid = (int)(((size_t)T * B + kPostThreads - 1) / kPostThreads);   // one thread per (t, b)
   unsigned char* mask = (unsigned char*)(w + L.mask);
   R* d_dynp = (R*)(w + L.dynp);
   if (pend) {
@@ -278,9 +280,15 @@ static int boxddp_impl(dmpc_handle h, int dtype, int T, int B, int n, int m, con
     CK(cudaMemcpyAsync(d_dynp, hp, sizeof(hp), cudaMemcpyHostToDevice, st));   // pageable: staged before the call returns
   }
   const int* skip = &dctl->done;
+  // Control records come back through page-locked memory and the NEXT block of iterations is enqueued before the host
+  // waits for the record of the current one, so the GPU never idles on the host; if the current block raised `done`, the
+  // kernels of the block already enqueued see the flag and return at once.
+  if (!h->pinned) CK(cudaHostAlloc(&h->pinned, 2 * sizeof(BoxDdpCtl), cudaHostAllocDefault));
+  for (int k = 0; k < 2; ++k) if (!h->ev[k]) CK(cudaEventCreateWithFlags(&h->ev[k], cudaEventDisableTiming));
+  BoxDdpCtl* hrec = (BoxDdpCtl*)h->pinned;
   BoxDdpCtl hc;
   memset(&hc, 0, sizeof(hc));
-  for (int i0 = 0; i0 < o->max_iter && !hc.done; i0 += poll) {
+  auto enqueue_block = [&](int i0, int slot) -> int {
     const int i1 = i0 + poll < o->max_iter ? i0 + poll : o->max_iter;
     for (int i = i0; i < i1; ++i) {
       // nominal trajectory and linearisation (box_ddp.py:123-131).  Pendulum: after iteration 0 the step's accepted
@@ -297,13 +305,28 @@ static int boxddp_impl(dmpc_handle h, int dtype, int T, int B, int n, int m, con
       if (rc) return rc;
       boxddp_norm_better_kernel<R><<<grid, tpb, 0, st>>>(T, B, m, i == 0, (R)o->best_cost_eps, u_cur, u_first, costs, flags, du,
                                                          (R*)costs_best, (R*)du_best, mask, dst, skip);
-      boxddp_post_kernel<R><<<pgrid, ptpb, 0, st>>>(T, B, n, m, x_new, u_new, mask, (R*)x_best, (R*)u_best, d_dynp,
-                                                    pend ? (R*)F_lin : nullptr, dst, dctl, i, o->eps, o->not_improved_lim);
+      boxddp_post_kernel<R><<<pgrid, kPostThreads, 0, st>>>(T, B, n, m, x_new, u_new, mask, (R*)x_best, (R*)u_best, d_dynp,
+                                                            pend ? (R*)F_lin : nullptr, dst, dctl, i, o->eps, o->not_improved_lim);
       h->launches += 2;
       R* t_ = u_cur; u_cur = u_new; u_new = t_;                     // next nominal controls = this step's controls
       if (pend) { t_ = x_nom; x_nom = x_new; x_new = t_; }          // ... and its rollout is the next nominal trajectory
     }
-    CK(cudaMemcpyAsync(&hc, dctl, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    if (cudaMemcpyAsync(&hrec[slot], dctl, sizeof(BoxDdpCtl), cudaMemcpyDeviceToHost, st) != cudaSuccess) return DMPC_ERR_CUDA;
+    if (cudaEventRecord(h->ev[slot], st) != cudaSuccess) return DMPC_ERR_CUDA;
+    return DMPC_OK;
+  };
+  if (o->max_iter > 0) {
+    int rc = enqueue_block(0, 0);
+    if (rc) return rc;
+    int slot = 0;
+    for (int i0 = 0; i0 < o->max_iter; i0 += poll) {
+      const bool more = i0 + poll < o->max_iter;
+      if (more) { rc = enqueue_block(i0 + poll, slot ^ 1); if (rc) return rc; }
+      CK(cudaEventSynchronize(h->ev[slot]));
+      hc = hrec[slot];
+      if (hc.done) break;
+      slot ^= 1;
+    }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
   }
@@ -363,6 +386,8 @@ int dmpc_destroy(dmpc_handle h) {
   if (!h) return DMPC_ERR_NULL;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  for (int i = 0; i < 2; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
   return DMPC_OK;
 }

@@ -228,6 +228,16 @@ __device__ __forceinline__ void g_lu_factor(const Grp<G>& g, int m, R* H, int ld
   }
 }
 
+// a / d.  An exactly-zero numerator (rows of clamped controls, active PNQP coordinates: they occur all the time) would
+// take the compiler's fp64 division down its out-of-line slow path (|a| < 6.6e-37; ~60 dependent instructions, and one
+// lane is enough to send the warp there); 0 / d = 0 * d for finite non-zero d, sign included.
+template <typename R>
+__device__ __forceinline__ R div_z(R a, R d) {
+  const R ad = fabs(d);
+  if (a == R(0) && ad > R(0) && ad < R(INFINITY)) return a * d;
+  return a / d;
+}
+
 // Back substitution U x = b for `ncols` columns of Rhs (in place); lane-per-column.
 template <int G, typename R>
 __device__ __forceinline__ void g_back_subst(const Grp<G>& g, int m, const R* H, int ldh,
@@ -236,7 +246,7 @@ __device__ __forceinline__ void g_back_subst(const Grp<G>& g, int m, const R* H,
     for (int i = m - 1; i >= 0; --i) {
       R acc = Rhs[i * ldr + j];
       for (int l = i + 1; l < m; ++l) acc -= H[i * ldh + l] * Rhs[l * ldr + j];
-      Rhs[i * ldr + j] = acc / H[i * ldh + i];
+      Rhs[i * ldr + j] = div_z(acc, H[i * ldh + i]);
     }
   }
 }
@@ -258,7 +268,7 @@ __device__ __forceinline__ void g_lu_solve(const Grp<G>& g, int m, const R* H, i
     for (int i = m - 1; i >= 0; --i) {
       R acc = Rhs[i * ldr + j];
       for (int l = i + 1; l < m; ++l) acc -= H[i * ldh + l] * Rhs[l * ldr + j];
-      Rhs[i * ldr + j] = acc / H[i * ldh + i];
+      Rhs[i * ldr + j] = div_z(acc, H[i * ldh + i]);
     }
   }
 }

@@ -87,7 +87,13 @@ __device__ __forceinline__ int g_pnqp(const Grp<SG>& sg, int m, const R* H, int 
     sg.sync();
     R n2 = R(0);
     for (int j = 0; j < m; ++j) n2 += rhs[j] * rhs[j];
-    bool large = sqrt(n2) >= R(DMPC_PNQP_TOL);      // pnqp.py:139-140
+    // pnqp.py:139-140 tests sqrt(|dx|^2) >= tol; away from the threshold |dx|^2 against tol^2 gives the same answer without
+    // the square root (whose n2 == 0 case - a converged, fully clamped QP - is the compiler's out-of-line slow path)
+    constexpr double mg2 = sizeof(R) == 8 ? 1e-13 : 1e-4;
+    bool large;
+    if (n2 >= R(DMPC_PNQP_TOL * DMPC_PNQP_TOL * (1.0 + mg2))) large = true;
+    else if (n2 <= R(DMPC_PNQP_TOL * DMPC_PNQP_TOL * (1.0 - mg2))) large = false;
+    else large = sqrt(n2) >= R(DMPC_PNQP_TOL);
     bool any_large = large;
     if (BATCH) any_large = batch_or(large ? 1 : 0, bphase) != 0;
     if (!any_large) break;                          // returns x *before* applying dx (Q4)
