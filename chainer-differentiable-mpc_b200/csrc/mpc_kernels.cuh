@@ -539,12 +539,19 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
         }
       }
       g.sync();
-      // objective 0.5 (tau^T C) tau + tau . c   (:251), every lane redundantly -> no reduction needed
-      R quad = R(0), lin = R(0);
-      for (int j = 0; j < s; ++j) {
+      R* tcol = chat;                                  // dead since the sweep: scratch for the column sums
+      // objective 0.5 (tau^T C) tau + tau . c   (:251).  The s column sums (tau^T C)_j are split over the lanes; the two
+      // length-s sums are then accumulated by every lane in the reference's order (same bits as the all-redundant loop,
+      // s + 2 s instead of s^2 + 2 s multiply-adds per lane)
+      for (int j = g.lane; j < s; j += G) {
         R tj = R(0);
         for (int i = 0; i < s; ++i) tj += tau[i] * Ct[i * s + j];
-        quad += tj * tau[j];
+        tcol[j] = tj;
+      }
+      g.sync();
+      R quad = R(0), lin = R(0);
+      for (int j = 0; j < s; ++j) {
+        quad += tcol[j] * tau[j];
         lin += tau[j] * ct[j];
       }
       const R obj = R(0.5) * quad + lin;

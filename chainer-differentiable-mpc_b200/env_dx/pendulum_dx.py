@@ -2,7 +2,9 @@
 
 Mirrors the solver-facing attributes of reference env_dx/pendulum.py:31-145 (PendulumDx) without
 Chainer or matplotlib: params (g, m, l), bounds, mpc_eps, line-search settings and get_true_obj().
-`forward(x, u)` evaluates the step on the GPU through dmpc_get_traj.
+`forward(x, u)` evaluates the step on the GPU through dmpc_get_traj.  The non-`simple` model (damping d, gravity bias b;
+pendulum.py:88-93) has no device code: its step is evaluated on the host and the solvers treat the object as an ordinary
+callable (plugin path).
 """
 import os
 import sys
@@ -22,14 +24,14 @@ class PendulumDx:
     _dmpc_dynamics = "pendulum"
 
     def __init__(self, params=None, simple=True):
-        assert simple, "only the simple model has device code"
-        self.simple = True
+        self.simple = bool(simple)
         self.max_torque = 2.0
         self.dt = 0.05
         self.n_state = 3
         self.n_ctrl = 1
-        self.params = np.array([10.0, 1.0, 1.0]) if params is None else np.asarray(params, dtype=np.float64)
-        assert len(self.params) == 3
+        default = [10.0, 1.0, 1.0] if self.simple else [10.0, 1.0, 1.0, 0.0, 0.0]      # g, m, l (, d, b)
+        self.params = np.array(default) if params is None else np.asarray(getattr(params, "array", params), dtype=np.float64)
+        assert len(self.params) == (3 if self.simple else 5)
         self.goal_state = np.array([1.0, 0.0, 0.0])
         self.goal_weights = np.array([1.0, 1.0, 0.1])
         self.ctrl_penalty = 0.001
@@ -40,12 +42,20 @@ class PendulumDx:
         self.max_linesearch_iter = 5
 
     def forward(self, x, u, device=0):
-        x = np.ascontiguousarray(x, dtype=np.float64)
-        u = np.ascontiguousarray(u, dtype=np.float64)
+        x = np.ascontiguousarray(getattr(x, "array", x), dtype=np.float64)
+        u = np.ascontiguousarray(getattr(u, "array", u), dtype=np.float64)
         squeeze = x.ndim == 1
         if squeeze:
             x, u = x[None], u[None]
         B = x.shape[0]
+        if not self.simple:                                   # pendulum.py:88-97, host arithmetic
+            g, m, l, d, b = self.params
+            uc = np.clip(u, -self.max_torque, self.max_torque)[:, 0]
+            th = np.arctan2(x[:, 1], x[:, 0])
+            newdth = x[:, 2] + self.dt * (-3.0 * g / (2.0 * l) * (-np.sin(th + b)) + 3.0 * uc / (m * l ** 2) - d * th)
+            newth = th + newdth * self.dt
+            r = np.stack((np.cos(newth), np.sin(newth), newdth), axis=1)
+            return r[0] if squeeze else r
         ctx = _native.default_context(device)
         out = ctx.empty((2, B, 3))
         uu = np.zeros((2, B, 1)); uu[0] = u

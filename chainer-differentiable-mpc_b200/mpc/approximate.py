@@ -12,7 +12,8 @@ Derivatives: the reference differentiates the callable with `chainer.grad` (appr
 Chainer (one that has `chainer.grad`) the same is done here; otherwise - the build image has no Chainer - central
 differences in float64, batched over B (2 s evaluations per timestep for a Jacobian, 2 s^2 + 1 for a Hessian), with steps
 cbrt(eps) / eps^(1/4) scaled by max(1, |tau_j|): relative error ~1e-10 / ~1e-7 on smooth callables, documented and
-tested as such (tests/test_gpu_generic_plugins.py), not bit-identical to autograd.
+tested as such (tests/test_gpu_generic_plugins.py), not bit-identical to autograd.  A kink inside the stencil (a clip in the
+dynamics exactly at a clamped control) is detected and resolved to the inclusive one-sided slope (`_fd_column`).
 """
 import os
 import sys
@@ -99,6 +100,18 @@ def approximate_cost(x, u, Cf):
 
 
 # -------------------------------------------------------------------------------------------- dynamics
+def _fd_column(f0, fp, fm, h):
+    """d f / d z_j from f(z), f(z + h e_j), f(z - h e_j): the central difference where the function is smooth.  Where the
+    one-sided differences disagree the stencil straddles a kink - in practice a clip inside the dynamics sitting exactly on
+    a clamped control - and the one-sided difference of larger magnitude is taken: that is the slope towards the inside of
+    the clip, the "inclusive" sub-gradient Chainer's F.clip (and the device pendulum's analytic Jacobian) use."""
+    fwd, bwd = (fp - f0) / h, (f0 - fm) / h
+    gap = np.abs(fwd - bwd)                                  # smooth: ~h |f''| ~ 1e-5; kink: the jump of the slope
+    kink = (gap > 1e-3 * (np.abs(fwd) + np.abs(bwd))) & (gap > 1e-4 * np.maximum(1.0, np.abs(f0)))
+    one_sided = np.where(np.abs(fwd) >= np.abs(bwd), fwd, bwd)
+    return np.where(kink, one_sided, (fp - fm) / (2.0 * h))
+
+
 def _jacobian_fd(dynamics, xt, ut):
     """(x_next [B,n], R [B,n,n], S [B,n,m]) of x_next = dynamics(x, u) by central differences."""
     B, n = xt.shape
@@ -108,10 +121,10 @@ def _jacobian_fd(dynamics, xt, ut):
     hx, hu = _steps(xt, FD_STEP_GRAD), _steps(ut, FD_STEP_GRAD)
     for j in range(n):
         e = np.zeros((B, n)); e[:, j] = hx[:, j]
-        R[:, :, j] = (_np(dynamics(xt + e, ut)) - _np(dynamics(xt - e, ut))) / (2.0 * hx[:, j, None])
+        R[:, :, j] = _fd_column(nx, _np(dynamics(xt + e, ut)), _np(dynamics(xt - e, ut)), hx[:, j, None])
     for j in range(m):
         e = np.zeros((B, m)); e[:, j] = hu[:, j]
-        S[:, :, j] = (_np(dynamics(xt, ut + e)) - _np(dynamics(xt, ut - e))) / (2.0 * hu[:, j, None])
+        S[:, :, j] = _fd_column(nx, _np(dynamics(xt, ut + e)), _np(dynamics(xt, ut - e)), hu[:, j, None])
     return nx, R, S
 
 

@@ -66,6 +66,7 @@ class BoxDDP(LinkBase):
             assert list(self.u_upper.shape) == list(shape)
         self.last_step = None
         self.info = None
+        self._dev_cache = None
 
     # ---- helpers -----------------------------------------------------------------------------
     def _rollout(self, ctx, x_init, u, dynamics):
@@ -132,6 +133,9 @@ class BoxDDP(LinkBase):
         if flags & _native.FLAG_LS_CAPPED:
             warnings.warn("MPCstep line search hit the %d-trial cap" % MAX_LS_TRIALS)
         best = dict(x=o["x"].download(), u=o["u"].download(), costs=o["costs"].download(), full_du_norm=o["du"].download())
+        # the final no-op MPCstep differentiates at exactly these tensors: keep the device copies for its backward
+        self._dev_cache = dict(C=dev_in[1], c=dev_in[2], lo=dev_in[3], hi=dev_in[4], x=o["x"], u=o["u"],
+                               F=(F_lin if F_lin is not None else dF))
         if F_lin is not None:
             large_f, f = F_lin.download()[:T - 1], f_lin.download()[:T - 1]
         else:
@@ -232,6 +236,8 @@ class BoxDDP(LinkBase):
         else:
             C_in, c_in = (cost.C, cost.c) if quad else (wrap(C_arr), wrap(c_arr))
             F_in, f_in = to_xp(F_in), to_xp(f_in)
+        if on_device and quad:
+            final._dev_cache = self._dev_cache       # same values as the host arrays handed to apply() below
         out = final.apply((x[0].copy(), C_in, c_in, F_in, f_in))
         x_new, u_new = out[0], out[1]
         self.last_step = final

@@ -42,7 +42,10 @@ def is_pendulum(dyn):
     """The package's pendulum_dx.PendulumDx (explicit `_dmpc_dynamics` marker) or the reference's
     env_dx.pendulum.PendulumDx (a chainer.Link: recognised by its class name AND the attributes the device code is a
     restatement of - n_state 3, n_ctrl 1, params, dt, max_torque); an unrelated class that merely shares the name is
-    not accepted."""
+    not accepted, and the non-`simple` model (damping / gravity bias, pendulum.py:88-93) has no device code: it is an
+    ordinary callable and takes the plugin path."""
+    if hasattr(dyn, "simple") and not dyn.simple:
+        return False
     if getattr(dyn, "_dmpc_dynamics", None) == "pendulum":
         return True
     return (type(dyn).__name__ == "PendulumDx" and getattr(dyn, "n_state", None) == 3 and getattr(dyn, "n_ctrl", None) == 1
@@ -51,8 +54,6 @@ def is_pendulum(dyn):
 
 def pendulum_params(dyn):
     """(g, m, l, dt, max_torque) handed to the device step (env_dx/pendulum.py:40-41,81-97)."""
-    if hasattr(dyn, "simple") and not dyn.simple:
-        raise NotImplementedError("only the `simple` pendulum model (g, m, l) has device code")
     p = np.asarray(to_xp(dyn.params), dtype=np.float64).ravel()
     dt, maxu = float(getattr(dyn, "dt", 0.05)), float(getattr(dyn, "max_torque", 2.0))
     assert dt > 0 and maxu > 0
@@ -113,6 +114,7 @@ class MPCstep(FunctionNodeBase):
         self.coupling = coupling
         self._ctx = _native.default_context(device)
         self._fwd = None       # retained host copies for backward
+        self._dev_cache = None # device copies of (C, c, F, x, u, lo, hi) a caller already holds (BoxDDP's device loop)
         self.aux = None        # extra kernel outputs (Ks, ks, alphas, free masks, ...)
 
     # ---- forward ---------------------------------------------------------------------------
@@ -330,6 +332,20 @@ class MPCstep(FunctionNodeBase):
         return x, u
 
     # ---- backward --------------------------------------------------------------------------
+    def _device_inputs(self, dt, C_hat, c_hat, F_hat, new_x, new_u, lo, hi):
+        """Device copies of the tensors the adjoint reads: the caller's (BoxDDP's device loop leaves them in HBM) when it
+        provided them for this dtype, uploads of the retained host arrays otherwise."""
+        host = dict(C=C_hat, c=c_hat, F=F_hat, x=new_x, u=new_u, lo=lo, hi=hi)
+        cache = self._dev_cache or {}
+        out = {}
+        for k, a in host.items():
+            d = cache.get(k)
+            if d is not None and d.dtype == np.dtype(dt) and int(np.prod(d.shape)) >= a.size:
+                out[k] = d
+            else:
+                out[k] = self._ctx.to_device(a)
+        return out
+
     def backward_numpy(self, dl_dx, dl_du):
         T, B, n, m, s = self.T, self.n_batch, self.n_state, self.n_ctrl, self.n_sc
         ctx = self._ctx
@@ -351,8 +367,8 @@ class MPCstep(FunctionNodeBase):
         dx0 = ctx.empty((B, n), dt); dC = ctx.empty((T, B, s, s), dt); dc = ctx.empty((T, B, s), dt)
         dF = ctx.empty((FT, B, n, s), dt)
         df = ctx.empty((T - 1, B, n), dt) if (f_hat is not None and T > 1) else None
-        ctx.mpc_step_backward(dt, T, B, n, m, ctx.to_device(C_hat), ctx.to_device(c_hat), ctx.to_device(F_hat), FT,
-                              ctx.to_device(new_x), ctx.to_device(new_u), ctx.to_device(lo), ctx.to_device(hi), gx, gu,
+        dv = self._device_inputs(dt, C_hat, c_hat, F_hat, new_x, new_u, lo, hi)
+        ctx.mpc_step_backward(dt, T, B, n, m, dv["C"], dv["c"], dv["F"], FT, dv["x"], dv["u"], dv["lo"], dv["hi"], gx, gu,
                               wsK, wsk, wsd, act, dx0, dC, dc, dF, df)
         self.active_index = act.download().astype(bool)
         return dx0.download(), dC.download(), dc.download(), dF.download(), (None if df is None else df.download())
@@ -375,9 +391,9 @@ class MPCstep(FunctionNodeBase):
         wsK = ctx.empty((T, B, m, n), dt); wsk = ctx.empty((T, B, m), dt); wsd = ctx.empty((T, B, s), dt)
         act = ctx.empty((T, B, m), np.uint8)
         part = ctx.empty((B, rsz), dt); sums = ctx.empty((rsz,), dt); dx0 = ctx.empty((B, n), dt)
-        ctx.mpc_step_backward_reduced(dt, T, B, n, m, ctx.to_device(C_hat), ctx.to_device(c_hat), ctx.to_device(F_hat),
-                                      F_hat.shape[0], ctx.to_device(new_x), ctx.to_device(new_u), ctx.to_device(lo),
-                                      ctx.to_device(hi), gx, gu, wsK, wsk, wsd, act, part, dx0, sums)
+        dv = self._device_inputs(dt, C_hat, c_hat, F_hat, new_x, new_u, lo, hi)
+        ctx.mpc_step_backward_reduced(dt, T, B, n, m, dv["C"], dv["c"], dv["F"], F_hat.shape[0], dv["x"], dv["u"], dv["lo"],
+                                      dv["hi"], gx, gu, wsK, wsk, wsd, act, part, dx0, sums)
         self.active_index = act.download().astype(bool)
         return (dx0.download(),) + _native.Context.split_reduced(sums.download(), n, m)
 

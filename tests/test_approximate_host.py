@@ -79,3 +79,22 @@ def test_lindx_passes_through():
     Fm, fm = np.ones((3, 2, 2, 3)), None
     F, f = linearize_dynamics(np.zeros((4, 2, 2)), np.zeros((4, 2, 1)), LinDx(Fm, fm))
     assert F is Fm and f is None
+
+
+def test_linearize_dynamics_resolves_the_clip_kink_like_the_analytic_jacobian():
+    """Controls sitting exactly on the pendulum's torque clip (+-2 = the MPC bounds): the stencil straddles the kink; the
+    inclusive slope is taken, as Chainer's F.clip and the analytic Jacobian do (oracle/pendulum.py `inside`)."""
+    from approximate import linearize_dynamics
+    from oracle import pendulum as pend
+    rs = np.random.RandomState(4)
+    T, B = 8, 5
+    th = rs.uniform(-np.pi / 2, np.pi / 2, B)
+    x0 = np.stack((np.cos(th), np.sin(th), rs.uniform(-1, 1, B)), axis=1)
+    u = rs.uniform(-1.5, 1.5, (T, B, 1))
+    u[1::2, ::2] = 2.0
+    u[::3, 1::2] = -2.0
+    x = np.zeros((T, B, 3)); x[0] = x0
+    F, f = (arr(v) for v in linearize_dynamics(x, u, lambda xs, us: pend.step(arr(xs), arr(us))))
+    F_ref, f_ref = pend.linearize(x0, u)
+    assert np.abs(F - F_ref).max() < 1e-4 and np.abs(f - f_ref).max() < 1e-4     # one-sided stencils are O(h) accurate
+    assert np.abs(F[:, :, 2, 3] - F_ref[:, :, 2, 3]).max() < 1e-6                # d(new dth)/du = 3 dt / (m l^2), not half of it
