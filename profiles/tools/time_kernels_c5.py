@@ -23,12 +23,17 @@ def fwd(flags):
 def bwd():
     ctx.lqr_adjoint(np.float64, T, B, n, m, P(pr["C"]), P(pr["c"]), P(pr["F"]), P(o["x"]), P(o["u"]), P(pr["gx"]), P(pr["gu"]),
                     P(o["Ks"]), P(o["fac"]), P(o["dx0"]), P(o["dC"]), P(o["dc"]), P(o["dF"]), P(o["df"]), 1, st.cuda_stream)
+rsz = ctx.reduced_grad_elems(n, m)
+o["part"] = torch.empty(B, rsz, dtype=f64, device=dev); o["sums"] = torch.empty(rsz, dtype=f64, device=dev)
+def bwd_red():
+    ctx.lqr_adjoint_reduced(np.float64, T, B, n, m, P(pr["C"]), P(pr["c"]), P(pr["F"]), P(o["x"]), P(o["u"]), P(pr["gx"]), P(pr["gu"]),
+                            P(o["Ks"]), P(o["fac"]), P(o["dc"]), P(o["part"]), P(o["dx0"]), P(o["sums"]), 1, st.cuda_stream)
 FULL = 7
-res = {"full": [], "factor": [], "bwd": []}
+res = {"full": [], "factor": [], "bwd": [], "bwd_reduced": []}
 for it in range(7):
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    e[0].record(st); fwd(FULL); e[1].record(st); fwd(5); e[2].record(st); bwd(); e[3].record(st)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    e[0].record(st); fwd(FULL); e[1].record(st); fwd(5); e[2].record(st); bwd(); e[3].record(st); bwd_red(); e[4].record(st)
     torch.cuda.synchronize()
     if it >= 2:
-        res["full"].append(e[0].elapsed_time(e[1])); res["factor"].append(e[1].elapsed_time(e[2])); res["bwd"].append(e[2].elapsed_time(e[3]))
+        res["full"].append(e[0].elapsed_time(e[1])); res["factor"].append(e[1].elapsed_time(e[2])); res["bwd"].append(e[2].elapsed_time(e[3])); res["bwd_reduced"].append(e[3].elapsed_time(e[4]))
 print(sys.argv[1] if len(sys.argv) > 1 else "", json.dumps({k: round(float(np.median(v)), 3) for k, v in res.items()}), "x_absmax", float(o["x"].abs().max()))
