@@ -652,25 +652,23 @@ __global__ void expand_time_batch_kernel(const R* __restrict__ src, R* __restric
     dst[o] = src[o % count];
 }
 
-// Second stage of ADJ_REDUCE_TB: out[o] = sum_e red[e][o] in a fixed order (strided partial sums, then a shuffle
-// tree) - deterministic, unlike atomics.  One warp per FOUR consecutive outputs: lane = 4 * (element slot) + (output
-// slot), so a warp-wide load touches 8 records x 32 contiguous bytes (whole sectors) instead of 32 sectors for 32 values.
+// Second stage of ADJ_REDUCE_TB: out[o] = sum_e red[e][o] in a fixed order (lane-strided partial sums, then a
+// shuffle tree) - deterministic, unlike atomics.  One warp per output element: the lanes' loads are rsz elements apart,
+// but neighbouring warps (outputs o, o+1, ...) read the same sectors at the same time and the L2 serves them - a variant
+// with one warp per four consecutive outputs (whole-sector loads, a quarter of the warps) measured 2.4x SLOWER at
+// rsz = 2952, B = 8192 (79 vs 33 us) and 3.6x slower at rsz = 35: the loop is latency bound and wants the warps.
 template <typename R>
 __global__ void reduce_partials_kernel(const R* red, int B, int rsz, R* out) {
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= rsz) return;
   const int lane = threadIdx.x & 31;
-  const int o = 4 * w + (lane & 3);
-  if (4 * w >= rsz) return;
-  const bool live = o < rsz;
   R a0 = R(0), a1 = R(0);
-  int e = lane >> 2;
-  if (live) {
-    for (; e + 8 < B; e += 16) { a0 += red[(size_t)e * rsz + o]; a1 += red[(size_t)(e + 8) * rsz + o]; }
-    if (e < B) a0 += red[(size_t)e * rsz + o];
-  }
+  int e = lane;
+  for (; e + 32 < B; e += 64) { a0 += red[(size_t)e * rsz + o]; a1 += red[(size_t)(e + 32) * rsz + o]; }
+  if (e < B) a0 += red[(size_t)e * rsz + o];
   R a = a0 + a1;
-  for (int d = 16; d >= 4; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
-  if (live && lane < 4) out[o] = a;
+  for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+  if (lane == 0) out[o] = a;
 }
 
 }  // namespace dmpc

@@ -137,8 +137,8 @@ int launch_adjoint_out(const AdjOutParams<R>& p, cudaStream_t st, long long* nl)
 
 template <typename R>
 int launch_reduce_partials(const R* red, int B, int rsz, R* out, cudaStream_t st, long long* nl) {
-  const int wpb = 4, warps = (rsz + 3) / 4;                 // one warp per four consecutive outputs
-  reduce_partials_kernel<R><<<(warps + wpb - 1) / wpb, wpb * 32, 0, st>>>(red, B, rsz, out);
+  const int wpb = 4;
+  reduce_partials_kernel<R><<<(rsz + wpb - 1) / wpb, wpb * 32, 0, st>>>(red, B, rsz, out);
   if (nl) ++*nl;
   return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;
 }

@@ -21,7 +21,7 @@ for _p in (_pkg, _here):
 import numpy as np  # noqa: E402
 
 import _native  # noqa: E402
-from _compat import HAVE_CHAINER, FunctionNodeBase, LinkBase, to_xp, wrap, as_f  # noqa: E402
+from _compat import HAVE_CHAINER, FunctionNodeBase, to_xp, wrap, as_f  # noqa: E402
 
 
 class DiffLqr(FunctionNodeBase):

@@ -24,7 +24,7 @@ for _p in (_pkg, _here, os.path.join(_pkg, "lqr")):
 import numpy as np  # noqa: E402
 
 import _native  # noqa: E402
-from _compat import HAVE_CHAINER, LinkBase, to_xp, wrap, as_f  # noqa: E402
+from _compat import LinkBase, to_xp, wrap, as_f  # noqa: E402
 from mpc_step import MPCstep, is_pendulum, pendulum_params  # noqa: E402
 from util import QuadCost, LinDx  # noqa: E402
 
