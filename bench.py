@@ -564,7 +564,10 @@ def run_b200(args):
             k2: {"ms": kt["adjoint_out"], "launches_per_step": 1, "algorithmic_bytes": Bc * (tot_b - fwd_b),
                  "role": ("adjoint sweep 2 (t up): d-tau rollout fused with lambda = V x + v, d-lambda = V dx + v' and " if fused_adj
                           else "lambda / d-lambda recursions + ") + "dC, dc, dF, df, dx0 (carries the adjoint's algorithmic bytes; "
-                         "the pair takes %.3f ms)" % kt["adjoint"]}}
+                         "the pair takes %.3f ms)" % kt["adjoint"] +
+                         ("; SURVEY 8(d)'s algorithmic figure counts a read of C_t, which the two-sweep adjoint does not need "
+                          "(lambda comes from the saved V_t, v_t), so hbm_frac on algorithmic bytes can exceed 1 while the measured "
+                          "DRAM traffic stays below the peak" if fused_adj else "")}}
         red_name = ("lqr_dtau_kernel<FUSED>+adjoint_fused_kernel<REDUCE_TB>+reduce_partials_kernel" if fused_adj else
                     "lqr_dtau_kernel+adjoint_out_kernel<REDUCE_TB>+reduce_partials_kernel")
         extra_kernels = {red_name: {
