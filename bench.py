@@ -78,7 +78,38 @@ class ClockSampler:
         self._stop = threading.Event()
         self._th = None
 
+    def _run_nvml(self):
+        """NVML through pynvml (nvidia-ml-py): microseconds per query, so a 0.3 s timed region yields dozens of samples
+        (an nvidia-smi subprocess takes ~0.3 s by itself).  Returns False when NVML is not usable."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        except Exception:
+            return False
+        bits = ((pynvml.nvmlClocksThrottleReasonHwSlowdown, 2), (pynvml.nvmlClocksThrottleReasonHwThermalSlowdown, 3),
+                (pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, 4), (pynvml.nvmlClocksThrottleReasonSwPowerCap, 5))
+        while not self._stop.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                row = [str(sm), str(mx), "Not Active", "Not Active", "Not Active", "Not Active"]
+                for bit, col in bits:
+                    if r & bit:
+                        row[col] = "Active"
+                self.rows.append(row)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+        return True
+
     def _run(self):
+        if self._run_nvml():
+            self.source = "nvml"
+            return
+        self.source = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
@@ -105,7 +136,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": getattr(self, "source", None)}
 
 
 def elem_rel_err(a, b, floor_frac=1e-3):
