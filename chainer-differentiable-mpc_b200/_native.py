@@ -56,6 +56,8 @@ SIGNATURES = {
     "dmpc_lqr_active_solve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dmpc_get_traj": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(_d), _vp, _vp, _vp, _vp]),
     "dmpc_expand_time_batch": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "dmpc_warmstart_take": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dmpc_warmstart_put": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dmpc_reduced_grad_elems": (_sz, [_i, _i]),
     "dmpc_lqr_adjoint_reduced": (_i, [_vp, _i, _i, _i, _i, _i] + [_vp] * 13 + [_i, _vp]),
     "dmpc_mpc_step_backward_reduced": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i] + [_vp] * 13 + [_vp]),
@@ -246,6 +248,39 @@ class PackedBuffers:
         self.base.free()
 
 
+class WarmStartCache:
+    """The warm-start cache of the reference's training loop (env_dx/il_exp.py:215-257: `train_warmstart[n_samples, T, m]`,
+    read with the minibatch's sample ids, written back with the solver's controls, zeroed every `restart_warmstart_every`
+    epochs) kept in HBM: `take(idxs)` returns the device tensor u_init[T, B, m] that BoxDDP accepts as is, `put(idxs, u)`
+    stores the device tensor BoxDDP leaves in `solver.u_device` - no host round trip of the controls."""
+
+    def __init__(self, ctx, n_samples, T, m, dtype=np.float64):
+        self.ctx, self.n_samples, self.T, self.m, self.dtype = ctx, int(n_samples), int(T), int(m), np.dtype(dtype)
+        self.cache = ctx.zeros((self.n_samples, self.T, self.m), self.dtype)
+
+    def reset(self):
+        self.cache.zero()
+
+    def _idx(self, idxs):
+        return self.ctx.to_device(np.ascontiguousarray(idxs, dtype=np.int32))
+
+    def take(self, idxs):
+        B = len(idxs)
+        u = self.ctx.empty((self.T, B, self.m), self.dtype)
+        self.ctx.warmstart_take(self.dtype, self.T, B, self.m, self.n_samples, self.cache, self._idx(idxs), u)
+        return u
+
+    def put(self, idxs, u):
+        B = len(idxs)
+        if not isinstance(u, DeviceArray):
+            u = self.ctx.to_device(np.ascontiguousarray(u, dtype=self.dtype))
+        assert tuple(u.shape) == (self.T, B, self.m) and u.dtype == self.dtype
+        self.ctx.warmstart_put(self.dtype, self.T, B, self.m, self.n_samples, self.cache, self._idx(idxs), u)
+
+    def download(self):
+        return self.cache.download()
+
+
 PACK_LIMIT_BYTES = 8 << 20      # above this the extra host-side staging copy costs more than the saved API calls
 
 
@@ -426,6 +461,12 @@ class Context:
 
     def reduced_grad_elems(self, n, m):
         return int(self.lib.dmpc_reduced_grad_elems(n, m))
+
+    def warmstart_take(self, dtype, T, B, m, n_samples, cache, idx, u, stream=None):
+        self._check(self.lib.dmpc_warmstart_take(self.h, dtype_code(dtype), T, B, m, n_samples, _p(cache), _p(idx), _p(u), stream))
+
+    def warmstart_put(self, dtype, T, B, m, n_samples, cache, idx, u, stream=None):
+        self._check(self.lib.dmpc_warmstart_put(self.h, dtype_code(dtype), T, B, m, n_samples, _p(cache), _p(idx), _p(u), stream))
 
     def boxddp_solve(self, dtype, T, B, n, m, x_init, C, c, lower, upper, dynamics, F, F_T, f, dyn_params, u_init,
                      eps, best_cost_eps, ls_decay, not_improved_lim, max_iter, max_ls_trials, coupling,

@@ -189,4 +189,20 @@ __global__ void __launch_bounds__(kPostThreads) boxddp_post_kernel(int T, int B,
   }
 }
 
+// ---- warm-start cache of controls in HBM (env_dx/il_exp.py:215-257 keeps train_warmstart[n_samples][T][m] on the host and
+// IL_Env.mpc transposes the gathered rows to [T][B][m], il_env.py:113).  take: u[t][b][:] = cache[idx[b]][t][:];
+// put: cache[idx[b]][t][:] = u[t][b][:].  One thread per (t, b, j); indices outside [0, n_samples) are skipped.
+template <typename R, bool PUT>
+__global__ void warmstart_kernel(int T, int B, int m, int n_samples, R* cache, const int* idx, R* u) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)T * B * m) return;
+  const int j = (int)(i % m);
+  const int b = (int)((i / m) % B);
+  const int t = (int)(i / ((size_t)m * B));
+  const int sidx = idx[b];
+  if (sidx < 0 || sidx >= n_samples) { if (!PUT) u[i] = R(0); return; }
+  R* c = cache + ((size_t)sidx * T + t) * m + j;
+  if (PUT) *c = u[i]; else u[i] = *c;
+}
+
 }  // namespace dmpc

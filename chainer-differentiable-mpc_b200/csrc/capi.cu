@@ -606,6 +606,37 @@ int dmpc_expand_time_batch(dmpc_handle h, int dtype, int T, int B, int count, co
   return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
 }
 
+static int warmstart_impl(dmpc_handle h, int dtype, int T, int B, int m, int n_samples, void* d_cache, const int* d_idx,
+                          void* d_u, bool put, void* stream) {
+  if (!h) return DMPC_ERR_NULL;
+  if (T < 1 || B < 1 || m < 1 || n_samples < 1) return fail(h, DMPC_ERR_BAD_SHAPE, "T,B,m,n_samples must be >= 1");
+  if (!d_cache || !d_idx || !d_u) return fail(h, DMPC_ERR_NULL, "warmstart: cache, idx and u are required");
+  if (set_dev(h)) return DMPC_ERR_CUDA;
+  cudaStream_t st = pick(h, stream);
+  const size_t total = (size_t)T * B * m;
+  const int tpb = 256;
+  const unsigned grid = (unsigned)((total + tpb - 1) / tpb);
+  if (dtype == DMPC_F64) {
+    if (put) warmstart_kernel<double, true><<<grid, tpb, 0, st>>>(T, B, m, n_samples, (double*)d_cache, d_idx, (double*)d_u);
+    else warmstart_kernel<double, false><<<grid, tpb, 0, st>>>(T, B, m, n_samples, (double*)d_cache, d_idx, (double*)d_u);
+  } else if (dtype == DMPC_F32) {
+    if (put) warmstart_kernel<float, true><<<grid, tpb, 0, st>>>(T, B, m, n_samples, (float*)d_cache, d_idx, (float*)d_u);
+    else warmstart_kernel<float, false><<<grid, tpb, 0, st>>>(T, B, m, n_samples, (float*)d_cache, d_idx, (float*)d_u);
+  } else return fail(h, DMPC_ERR_UNSUPPORTED, "dtype");
+  ++h->launches;
+  return cudaGetLastError() == cudaSuccess ? DMPC_OK : fail(h, DMPC_ERR_CUDA, "warmstart launch failed");
+}
+
+int dmpc_warmstart_take(dmpc_handle h, int dtype, int T, int B, int m, int n_samples, const void* d_cache, const int32_t* d_idx,
+                        void* d_u, void* stream) {
+  return warmstart_impl(h, dtype, T, B, m, n_samples, const_cast<void*>(d_cache), (const int*)d_idx, d_u, false, stream);
+}
+
+int dmpc_warmstart_put(dmpc_handle h, int dtype, int T, int B, int m, int n_samples, void* d_cache, const int32_t* d_idx,
+                       const void* d_u, void* stream) {
+  return warmstart_impl(h, dtype, T, B, m, n_samples, d_cache, (const int*)d_idx, const_cast<void*>(d_u), true, stream);
+}
+
 size_t dmpc_reduced_grad_elems(int n, int m) { return (size_t)adj_red_elems(n, m); }
 
 int dmpc_lqr_adjoint_reduced(dmpc_handle h, int dtype, int T, int B, int n, int m, const void* d_C, const void* d_c,

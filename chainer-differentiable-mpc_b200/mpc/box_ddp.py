@@ -67,6 +67,7 @@ class BoxDDP(LinkBase):
         self.last_step = None
         self.info = None
         self._dev_cache = None
+        self.u_device = None
 
     # ---- helpers -----------------------------------------------------------------------------
     def _rollout(self, ctx, x_init, u, dynamics):
@@ -113,7 +114,8 @@ class BoxDDP(LinkBase):
         coupling = resolve_coupling(self.coupling, B, n, m)
         o = dict(x=ctx.empty((T, B, n), dt), u=ctx.empty((T, B, m), dt), costs=ctx.empty((B,), dt),
                  du=ctx.empty((B,), dt), du_last=ctx.empty((B,), dt))
-        dev_in = [ctx.to_device(a) for a in (x_init, C_arr, c_arr, self.u_lower, self.u_upper, u)]
+        dev_in = [a if isinstance(a, _native.DeviceArray) else ctx.to_device(a)
+                  for a in (x_init, C_arr, c_arr, self.u_lower, self.u_upper, u)]
 
         def solve(cpl):
             return ctx.boxddp_solve(
@@ -133,6 +135,7 @@ class BoxDDP(LinkBase):
         if flags & _native.FLAG_LS_CAPPED:
             warnings.warn("MPCstep line search hit the %d-trial cap" % MAX_LS_TRIALS)
         best = dict(x=o["x"].download(), u=o["u"].download(), costs=o["costs"].download(), full_du_norm=o["du"].download())
+        self.u_device = o["u"]          # best controls, still in HBM: what _native.WarmStartCache.put takes
         # the final no-op MPCstep differentiates at exactly these tensors: keep the device copies for its backward
         self._dev_cache = dict(C=dev_in[1], c=dev_in[2], lo=dev_in[3], hi=dev_in[4], x=o["x"], u=o["u"],
                                F=(F_lin if F_lin is not None else dF))
@@ -154,14 +157,20 @@ class BoxDDP(LinkBase):
         if plugin and not (isinstance(dynamics, LinDx) or callable(dynamics)):
             raise TypeError("dynamics must be a util.LinDx, a PendulumDx or a callable (x[B,n], u[B,m]) -> x_next[B,n]")
         ctx = _native.default_context(self.device)
-        if self.u_init is None:
+        u_dev = None
+        if isinstance(self.u_init, _native.DeviceArray):            # warm start already in HBM (_native.WarmStartCache)
+            u_dev = self.u_init
+            assert list(u_dev.shape) == [T, B, m] and u_dev.dtype == np.float64, "device u_init must be float64 [T,B,m]"
+            u = None
+        elif self.u_init is None:
             u = np.zeros((T, B, m))
         else:
             u = np.asarray(to_xp(self.u_init), dtype=np.float64)
             if list(u.shape) == [T, m]:
                 u = np.repeat(u[:, None, :], B, axis=1)
-        assert list(u.shape) == [T, B, m], "u dim mismatch, actual" + str(u.shape)
-        assert not np.isnan(u).any()
+        if u is not None:
+            assert list(u.shape) == [T, B, m], "u dim mismatch, actual" + str(u.shape)
+            assert not np.isnan(u).any()
         if quad:
             C_arr, c_arr = as_f(cost.C, np.float64), as_f(cost.c, np.float64)
             true_cost = QuadCost(C_arr, c_arr)
@@ -178,8 +187,11 @@ class BoxDDP(LinkBase):
         status = "max_iter"
         n_iter = 0
         on_device = self.device_loop and not self.verbose and not self.ilqr_verbose and not plugin
+        if u is None and not on_device:
+            u = u_dev.download()                                       # the host loop iterates on host arrays
         if on_device:
-            best, du_last, n_iter, status, large_f, f = self._solve_on_device(ctx, x_init, C_arr, c_arr, true_dyn, u)
+            best, du_last, n_iter, status, large_f, f = self._solve_on_device(ctx, x_init, C_arr, c_arr, true_dyn,
+                                                                             u_dev if u_dev is not None else u)
             print({"converged": "Converged", "not_improved": "Not improved lim", "max_iter": "Not Converged "}[status])
         for i in range(0 if on_device else self.max_iter):
             n_iter = i + 1

@@ -3,7 +3,8 @@ env_dx/il_exp.py:230-302 + env_dx/il_env.py:104-158 + env_dx/pendulum_net.py:18-
 
     q = sigmoid(q_logit),  p = sqrt(q) * learn_p                       (Pendulum_Net_cost_logit.forward)
     Q, p repeated to [T,B,4,4] / [T,B,4]; BoxDDP(eps 1e-3, max_iter 500, decay 0.2, 5 line-search trials,
-    update_dynamics=False, exit_unconverged=False, detach_unconverged=True), warm-started from the last controls  (IL_Env.mpc)
+    update_dynamics=False, exit_unconverged=False, detach_unconverged=True), warm-started from the last controls  (IL_Env.mpc);
+    the warm-start cache of il_exp.py:215-257 (controls per sample id) lives in HBM (_native.WarmStartCache)
     loss = mean((u_expert - u)^2); backward through the final MPCstep; RMSprop(lr 1e-2, alpha 0.5),
     p and q updated in alternating blocks of 10 iterations                                              (IL_Exp.run)
 
@@ -86,7 +87,9 @@ def main():
     q_logit, learn_p = np.zeros(4), np.zeros(4)                # pendulum_net.py:22-25
     ms = {"q": np.zeros(4), "p": np.zeros(4)}
     lr, alpha, eps = 1e-2, 0.5, 1e-8                           # chainer.optimizers.RMSprop(lr=1e-2, alpha=0.5), il_exp.py:213
-    warm = np.zeros((T, B, 1))
+    import _native
+    cache = _native.WarmStartCache(_native.default_context(local), B, T, 1)    # il_exp.py:215: zeros, one row per sample id
+    ids = np.arange(B)
     update_q = False
     hist = []
     t_start = time.perf_counter()
@@ -95,8 +98,8 @@ def main():
             update_q = not update_q
         q = 1.0 / (1.0 + np.exp(-q_logit))
         p = np.sqrt(q) * learn_p
-        u, solver = mpc(dx, x0, q, p, warm, local)
-        warm = u.copy()
+        u, solver = mpc(dx, x0, q, p, cache.take(ids), local)     # il_exp.py:249: warm start of this minibatch, on the device
+        cache.put(ids, solver.u_device)                            # il_exp.py:257, without a host round trip
         diff = u - u_exp
         loss_sum = float(np.sum(diff * diff))
         gu = 2.0 * diff / (args.batch * T)                     # d mean((u_exp-u)^2) / du over the GLOBAL batch

@@ -22,6 +22,9 @@
  *     dmpc_create() returns DMPC_ERR_NO_DEVICE.
  *   - Inputs are never modified (pnqp.py:86, util.py:496,514 make copies);
  *     the caller owns every buffer.
+ *   - Threads: the library keeps no global state; a handle carries a stream, a launch counter, the last error text and
+ *     (dmpc_boxddp_solve) a small pinned record, so ONE thread at a time may use a given handle.  Different handles - also
+ *     on the same device - may be used concurrently (bench.py's e2e feeders hold one each).
  */
 #ifndef DIFFMPC_B200_H
 #define DIFFMPC_B200_H
@@ -277,6 +280,16 @@ int dmpc_boxddp_solve(dmpc_handle h, int dtype, int T, int B, int n, int m,
  * mpc_net.py:78-80, il_env.py:120-129): d_dst[t][b][0..count) = d_src[0..count) for t < T, b < B.  The forward half of the
  * shared-parameter path; its backward is the fused (T,B)-sum of dmpc_*_reduced below. */
 int dmpc_expand_time_batch(dmpc_handle h, int dtype, int T, int B, int count, const void* d_src, void* d_dst, void* stream);
+
+/* Warm-start cache of controls in HBM (reference env_dx/il_exp.py:215-257: train_warmstart[n_samples][T][m] indexed by the
+ * sample ids of the minibatch; IL_Env.mpc transposes the gathered rows to [T][B][m], il_env.py:113).
+ *   take: d_u[t][b][:] = d_cache[d_idx[b]][t][:]      put: d_cache[d_idx[b]][t][:] = d_u[t][b][:]
+ * d_idx[B] int32 sample ids; ids outside [0, n_samples) read as zeros / are not written.  With dmpc_boxddp_solve taking
+ * d_u_init and returning d_u_best on the device, a training loop keeps its warm starts resident (no PCIe round trip). */
+int dmpc_warmstart_take(dmpc_handle h, int dtype, int T, int B, int m, int n_samples, const void* d_cache,
+                        const int32_t* d_idx, void* d_u, void* stream);
+int dmpc_warmstart_put(dmpc_handle h, int dtype, int T, int B, int m, int n_samples, void* d_cache,
+                       const int32_t* d_idx, const void* d_u, void* stream);
 
 size_t dmpc_reduced_grad_elems(int n, int m);
 int dmpc_lqr_adjoint_reduced(dmpc_handle h, int dtype, int T, int B, int n, int m,

@@ -227,3 +227,45 @@ def test_boxddp_and_backward_against_exact_qp():
         fp = (ex._loss(ex._solve_exact(q, p + e, pr, sets)[3], pr) - ex._loss(ex._solve_exact(q, p - e, pr, sets)[3], pr)) / (2 * h)
         assert abs(gq[i] - fq) <= 2e-3 * abs(fq) + 2e-6, ("q", i, gq[i], fq)
         assert abs(gp[i] - fp) <= 2e-3 * abs(fp) + 2e-6, ("p", i, gp[i], fp)
+
+
+def test_warmstart_cache_on_the_device():
+    """The warm-start cache of il_exp.py:215-257 kept in HBM: take / put against numpy fancy indexing + the transpose of
+    il_env.py:113, out-of-range ids, and BoxDDP taking the device tensor as u_init and leaving its controls on the device."""
+    import _native
+    from box_ddp import BoxDDP
+    from util import QuadCost
+    from pendulum_dx import PendulumDx
+    ctx = _native.default_context(0)
+    rs = np.random.RandomState(0)
+    n_samples, T, m, B = 50, 20, 1, 16
+    cache = _native.WarmStartCache(ctx, n_samples, T, m)
+    host = np.zeros((n_samples, T, m))
+    idxs = rs.permutation(n_samples)[:B]
+    u = rs.randn(T, B, m)
+    cache.put(idxs, u)
+    host[idxs] = np.transpose(u, (1, 0, 2))
+    assert np.array_equal(cache.download(), host)
+    idx2 = np.concatenate((idxs[::2], [n_samples + 3, -1], rs.permutation(n_samples)[:6]))
+    got = cache.take(idx2).download()
+    ref = np.zeros((T, len(idx2), m))
+    ok = (idx2 >= 0) & (idx2 < n_samples)
+    ref[:, ok] = np.transpose(host[idx2[ok]], (1, 0, 2))
+    assert np.array_equal(got, ref)
+    # BoxDDP: device warm start == host warm start, bit for bit; its controls go back into the cache without a download
+    th = rs.rand(B) * np.pi - np.pi / 2
+    x0 = np.stack((np.cos(th), np.sin(th), rs.rand(B) * 2 - 1), axis=1)
+    dx = PendulumDx(); qv, pv = dx.get_true_obj()
+    Q = np.repeat(np.repeat(np.diag(qv)[None, None], T, 0), B, 1); p = np.repeat(np.repeat(pv[None, None], T, 0), B, 1)
+    warm = np.clip(0.3 * rs.randn(T, B, m), -2, 2)
+    cache.reset(); cache.put(idxs, warm)
+    kw = dict(T=T, u_lower=-2.0, u_upper=2.0, n_batch=B, n_state=3, n_ctrl=1, eps=1e-3, max_iter=12, exit_unconverged=False,
+              line_search_decay=0.2, max_line_search_iter=5, update_dynamics=False)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = BoxDDP(u_init=warm, **kw); xa, ua, ca = a((x0, QuadCost(Q, p), dx))
+        b = BoxDDP(u_init=cache.take(idxs), **kw); xb, ub, cb = b((x0, QuadCost(Q, p), dx))
+    assert np.array_equal(arr(ua), arr(ub)) and np.array_equal(arr(xa), arr(xb)) and np.array_equal(ca, cb)
+    cache.put(idxs, b.u_device)
+    assert np.array_equal(cache.download()[idxs], np.transpose(arr(ub), (1, 0, 2)))
+    assert np.array_equal(b.u_device.download(), arr(ub))
