@@ -59,6 +59,32 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_fingerprint():
+    """sha256 of the config-5 kernel sources with comments and whitespace removed: traffic.json records the value at
+    capture time, so a kernel change after the ncu capture shows up as roofline.traffic_stale instead of going unnoticed."""
+    import hashlib
+    import re
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "chainer-differentiable-mpc_b200", "csrc")
+    for name in ("lqr_dmma_warp.cuh", "lqr_dmma_launch.cu", "lqr_adjoint_fused.cuh", "lqr_kernels.cuh"):
+        try:
+            src = open(os.path.join(d, name)).read()
+        except OSError:
+            return None
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        h.update(re.sub(r"\s+", "", src).encode())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic_fingerprint():
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2", "traffic.json")) as fh:
+            return json.load(fh).get("_kernel_fingerprint")
+    except Exception:
+        return None
+
+
 def ncu_traffic():
     """Measured DRAM bytes per solve of each kernel (one ncu --set full capture each, committed under profiles/)."""
     path = os.path.join(ROOT, "profiles", "r2", "traffic.json")
@@ -637,7 +663,9 @@ def run_b200(args):
                      "chunk_batch": Bc,
                      "whole_step_achieved_gbs": whole, "whole_step_hbm_frac": whole / peak,
                      "algorithmic_bytes_per_solve": {"fwd": fwd_b, "fwd_bwd": tot_b},
-                     "traffic_source": "ncu dram__bytes_read+write per solve x launch batch (profiles/r2/traffic.json)"})
+                     "traffic_source": "ncu dram__bytes_read+write per solve x launch batch (profiles/r2/traffic.json)",
+                     # true when the kernel sources differ from the ones the ncu capture was taken with
+                     "traffic_stale": (ncu_traffic_fingerprint() is not None and ncu_traffic_fingerprint() != kernel_fingerprint())})
         line = {"metric": "lqr_fwd_bwd_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
