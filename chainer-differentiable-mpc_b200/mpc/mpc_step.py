@@ -32,7 +32,45 @@ from _compat import FunctionNodeBase, to_xp, wrap, as_f  # noqa: E402
 from util import QuadCost, LinDx  # noqa: E402
 
 LqrBackOut = namedtuple("lqrBackOut", "n_total_qp_iter")
-LqrForOut = namedtuple("lqrForOut", "objs full_du_norm alpha_du_norm mean_alphas costs")
+_LqrForOutT = namedtuple("lqrForOut", "objs full_du_norm alpha_du_norm mean_alphas costs")
+
+
+class LqrForOut:
+    """The reference's lqrForOut namedtuple (mpc_step.py:25-30), with the two batch-scrambled step norms evaluated on first
+    use: they are two transposed reductions over [T,B,m] that a caller of a single MPC step (and the latency path) often
+    never reads.  Attribute access, indexing, iteration and len() behave like the namedtuple's."""
+    _fields = _LqrForOutT._fields
+
+    def __init__(self, objs, full_du_norm, alpha_du_norm, mean_alphas, costs):
+        self.objs, self.mean_alphas, self.costs = objs, mean_alphas, costs
+        self._full, self._alpha = full_du_norm, alpha_du_norm          # arrays, or zero-argument callables
+
+    @property
+    def full_du_norm(self):
+        if callable(self._full):
+            self._full = self._full()
+        return self._full
+
+    @property
+    def alpha_du_norm(self):
+        if callable(self._alpha):
+            self._alpha = self._alpha()
+        return self._alpha
+
+    def _astuple(self):
+        return _LqrForOutT(self.objs, self.full_du_norm, self.alpha_du_norm, self.mean_alphas, self.costs)
+
+    def __iter__(self):
+        return iter(self._astuple())
+
+    def __getitem__(self, i):
+        return self._astuple()[i]
+
+    def __len__(self):
+        return 5
+
+    def __repr__(self):
+        return repr(self._astuple())
 
 DEFAULT_COUPLING = "auto"     # 'batch' | 'element' | 'auto' (see pnqp.py)
 MAX_LS_TRIALS = 64            # safety cap of the per-element line search (reference has none, Q5)
@@ -133,7 +171,7 @@ class MPCstep(FunctionNodeBase):
             assert list(f_hat.shape) in ([T - 1, B, n], [T, B, n]), " f_hat dim mismatch"
         u_nom, x_nom = as_f(self.controls, dt), as_f(self.current_states, dt)
         lo, hi = as_f(self.u_lower, dt), as_f(self.u_upper, dt)
-        assert not np.isnan(u_nom).any() and not np.isnan(lo).any() and not np.isnan(hi).any()
+        assert not (np.isnan(np.min(u_nom)) or np.isnan(np.min(lo)) or np.isnan(np.min(hi)))    # min propagates NaN
         assert (lo <= hi).all(), " lower is larger than upper"
         if self._is_plugin():
             return self._forward_plugin(C_hat, c_hat, F_hat, f_hat, x_nom, u_nom, lo, hi)
@@ -204,10 +242,11 @@ class MPCstep(FunctionNodeBase):
         if (flags & _native.FLAG_LS_CAPPED).any():
             warnings.warn("MPCstep line search hit the %d-trial cap on %d elements" % (MAX_LS_TRIALS, int((flags & 4).astype(bool).sum())))
         x, u = r["x"], r["u"]
-        assert not np.isnan(x).any() and not np.isnan(u).any()     # reference :284-285
+        assert not (np.isnan(np.min(x)) or np.isnan(np.min(u)))     # reference :284-285
         self.back_out = LqrBackOut(n_total_qp_iter=int(r["n_qp"].max(axis=1).sum()))
-        self.for_out = LqrForOut(r["objs"], scrambled_norm(u_nom - r["u_first"], B, T, m),
-                                 scrambled_norm(u_nom - u, B, T, m), np.mean(r["alphas"]), r["costs"])
+        u_first = r["u_first"]
+        self.for_out = LqrForOut(r["objs"], lambda: scrambled_norm(u_nom - u_first, B, T, m),
+                                 lambda: scrambled_norm(u_nom - u, B, T, m), np.mean(r["alphas"]), r["costs"])
         self.aux = dict(Ks=r["Ks"], ks=r["ks"], alphas=r["alphas"], free=r["free"], n_qp=r["n_qp"], n_ls=r["n_ls"],
                         old_costs=r["old"], coupling=coupling, u_first=r["u_first"])
         return x, u
