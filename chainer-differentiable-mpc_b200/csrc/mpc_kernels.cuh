@@ -489,11 +489,12 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
   }
 
   // =========================== forward_rec (mpc_step.py:175-286) ===========================
-  // pass -1 evaluates the cost of the nominal trajectory (xpget_cost, :191); passes >= 0 are the
-  // line-search trials with alpha = ls_decay^pass until cost <= old cost (Q5).
+  // Passes are the line-search trials with alpha = ls_decay^pass until cost <= old cost (Q5).  The cost of the nominal
+  // trajectory (xpget_cost, :191) is evaluated inside the first pass, on the same C_t, c_t tiles: a separate pass for it
+  // re-read every tile of the horizon (one third of this phase's DRAM traffic and barrier chain at ~1 trial per element).
   const bool linear = p.dynamics == DMPC_DYN_LINEAR;
   R alpha = R(1), old_cost = R(0), cost = R(0);
-  int trial = -1;
+  int trial = 0;
   bool done = false;
   while (!done) {
     auto load_tiles = [&](int t, int st) {
@@ -524,9 +525,7 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
       const R* Ct = base + L.oC; const R* ct = base + L.oc; const R* Ft = base + L.oF; const R* ft = base + L.of_;
       const R* xn = base + L.oxn; const R* un = base + L.oun; const R* lot = base + L.olo; const R* hit = base + L.ohi;
       const R* Kt = base + L.oK; const R* kt = base + L.ok;
-      if (trial < 0) {
-        for (int o = g.lane; o < s; o += G) tau[o] = (o < n) ? xn[o] : un[o - n];
-      } else {
+      {
         if (t == 0) for (int o = g.lane; o < n; o += G) xnew[o] = xn[o];       // new_x[0] = states[0]
         g.sync();
         for (int o = g.lane; o < n; o += G) { tau[o] = xnew[o]; dxv[o] = (t == 0) ? R(0) : xnew[o] - xn[o]; }
@@ -543,10 +542,17 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
       // objective 0.5 (tau^T C) tau + tau . c   (:251).  The s column sums (tau^T C)_j are split over the lanes; the two
       // length-s sums are then accumulated by every lane in the reference's order (same bits as the all-redundant loop,
       // s + 2 s instead of s^2 + 2 s multiply-adds per lane)
+      const bool first = trial == 0;                   // this pass also evaluates the nominal trajectory (x_nom, u_nom)
+      R* tcol0 = Rhs;                                  // dead since the sweep, m (n + 1) >= s entries
       for (int j = g.lane; j < s; j += G) {
-        R tj = R(0);
-        for (int i = 0; i < s; ++i) tj += tau[i] * Ct[i * s + j];
+        R tj = R(0), tj0 = R(0);
+        for (int i = 0; i < s; ++i) {
+          const R cij = Ct[i * s + j];
+          tj += tau[i] * cij;
+          if (first) tj0 += ((i < n) ? xn[i] : un[i - n]) * cij;
+        }
         tcol[j] = tj;
+        if (first) tcol0[j] = tj0;
       }
       g.sync();
       R quad = R(0), lin = R(0);
@@ -556,7 +562,16 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
       }
       const R obj = R(0.5) * quad + lin;
       cost += obj;
-      if (trial >= 0) {
+      if (first) {
+        R quad0 = R(0), lin0 = R(0);
+        for (int j = 0; j < s; ++j) {
+          const R tn = (j < n) ? xn[j] : un[j - n];
+          quad0 += tcol0[j] * tn;
+          lin0 += tn * ct[j];
+        }
+        old_cost += R(0.5) * quad0 + lin0;
+      }
+      {
         const size_t idx = (size_t)t * tb + e;
         if (valid) {
           for (int o = g.lane; o < n; o += G) p.x[idx * n + o] = tau[o];
@@ -579,10 +594,7 @@ __global__ void mpc_forward_kernel(MpcFwdParams<R> p) {
       g.sync();
       st ^= 1;
     }
-    if (trial < 0) {
-      old_cost = cost;
-      trial = 0;
-    } else {
+    {
       const bool worse = cost > old_cost;             // NaN -> accepted, as in the reference
       if (!worse) done = true;
       else if (trial + 1 >= p.max_ls_trials) { status |= FLAG_LS_CAPPED; ++trial; done = true; }   // alpha stays the one of the
