@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include <type_traits>
 #include "launch.h"
+#include "lqr_tpe_kernel.cuh"
 
 #ifndef DMPC_REAL
 #define DMPC_REAL double
@@ -45,6 +46,12 @@ static bool dmma_enabled() {
   return v == 1;
 }
 
+static bool lqr_tpe_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DMPC_LQR_GROUP"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 template <typename R>
 int launch_lqr_rollout_32_8(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
   LqrParams<R> q = p;
@@ -63,6 +70,22 @@ int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
   const bool aligned = al16(p.C) && al16(p.c) && al16(p.F) && al16(p.f) && al16(p.Ks) && al16(p.ks) && al16(p.fac) && al16(p.Vsave);
   if (p.n == 32 && p.m == 8 && !(p.flags & LQR_MASKED) && p.c && p.c_scale == R(1) && dmma_enabled() && aligned)
     return launch_lqr_solve_dmma<R>(p, st, nl);
+  // s <= 6: one thread per element, registers only (lqr_tpe_kernel.cuh); DMPC_LQR_GROUP=1 keeps the group kernel (A/B)
+  if (lqr_tpe_enabled()) {
+    const int tpb = p.B >= 148 * 64 * 2 ? 64 : 32;            // small batches: more, smaller CTAs so the grid covers the SMs
+    const int grid = (p.B + tpb - 1) / tpb;
+#define X(N_, M_)                                                                                            \
+    if (p.n == N_ && p.m == M_) {                                                                            \
+      auto k = lqr_tpe_kernel<R, N_, M_, 64>;                                                                \
+      const size_t sm = (size_t)(tpb / 32) * tpe_lqr_warp_reals(N_, M_) * sizeof(R);                         \
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA; \
+      k<<<grid, tpb, sm, st>>>(p);                                                                           \
+      if (nl) ++*nl;                                                                                         \
+      return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;                                    \
+    }
+    X(2, 1) X(3, 1) X(4, 2)
+#undef X
+  }
   const bool compact = !(p.flags & LQR_DO_FACTOR);
   const LqrLayout L = lqr_layout<R>(p.n, p.m, (p.flags & LQR_SAVE_FAC) != 0, compact);
   const size_t sb = (size_t)L.stride * sizeof(R);

@@ -1,0 +1,307 @@
+// LqrRecursion.backward + .forward (reference lqr/lqr_recursion.py:69-200) and LQR_active (reference
+// mpc/active_constrained_lqr.py:67-193) for SMALL systems - s = n + m <= 6: the pendulum / Boyd / LQRnet shape (3,1), the
+// one-variable example (2,1) and BASELINE config 2 (4,2) - with ONE THREAD per batch element and the whole recursion in
+// registers.
+//
+// Why: lqr_solve_kernel gives such an element a group of 4-8 lanes that exchange every intermediate through shared
+// memory, with seven group barriers and a generic LU per time step; at s = 6 a Riccati step is ~700 flops, and the group
+// kernel spends ~7900 cycles on it (profiles/r2/r2y_bench_c2.json: 0.201 ms for T = 50) - dependent-chain latency, not
+// bandwidth (7 % of HBM).  A thread that owns the element needs no barrier, no shared memory, and its m <= 2 elimination
+// is a handful of FMAs.  Same contract as lqr_solve_kernel (LqrParams, every flag), same operation order where rounding
+// could matter to a caller comparing runs (pivoting: first maximum wins; multipliers through the pivot's reciprocal;
+// back substitution by division).
+#pragma once
+#include "lqr_kernels.cuh"
+
+namespace dmpc {
+
+// in-register pivoted Gaussian elimination H X = Rhs (H: M x M, Rhs: M x NC), M <= 2; X overwrites Rhs
+template <typename R, int M, int NC>
+__device__ __forceinline__ void tpe_solve(R (&H)[M][M], R (&X)[M][NC]) {
+  if constexpr (M == 2) {
+    if (fabs(H[1][0]) > fabs(H[0][0])) {                     // first maximum wins (LAPACK idamax)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { const R t = H[0][j]; H[0][j] = H[1][j]; H[1][j] = t; }
+#pragma unroll
+      for (int j = 0; j < NC; ++j) { const R t = X[0][j]; X[0][j] = X[1][j]; X[1][j] = t; }
+    }
+    const R l = H[1][0] * (R(1) / H[0][0]);
+    H[1][1] -= l * H[0][1];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) X[1][j] -= l * X[0][j];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      X[1][j] = div_z(X[1][j], H[1][1]);
+      X[0][j] = div_z(X[0][j] - H[0][1] * X[1][j], H[0][0]);
+    }
+  } else {
+    static_assert(M == 1, "tpe_solve: m <= 2");
+#pragma unroll
+    for (int j = 0; j < NC; ++j) X[0][j] = div_z(X[0][j], H[0][0]);
+  }
+}
+
+// Operand staging.  Elements e0 .. e0+31 of one time step are CONTIGUOUS in the reference layout ([T][B][...]), but a
+// thread that loads its own element directly touches a different 128-byte line than its neighbour: every LDG is 32
+// separate L1 requests and the step is bound by the load pipe and by exposed DRAM latency (measured: the first version of
+// this kernel, direct loads + L2 prefetch, 0.179 ms against the group kernel's 0.201 ms at config 2).  So the WARP copies
+// the step's operands of its 32 elements with coalesced cp.async into a ring of shared-memory stages (one slot per
+// element, odd stride: conflict-free reads), one step ahead in the Riccati sweep and two in the rollout.
+template <typename R>
+__device__ __forceinline__ void tpe_cp(R* sdst, const R* g) {
+  if (sizeof(R) == 8) cp_async8(sdst, g); else cp_async4(sdst, g);
+}
+// `cnt` reals per element for `nv` consecutive elements -> slot[le * stride + off + j]
+template <typename R>
+__device__ __forceinline__ void tpe_stage(R* dst, int stride, int off, const R* src, int cnt, int nv, int lane) {
+  const int total = nv * cnt;
+  for (int i = lane; i < total; i += 32) { const int le = i / cnt, j = i - le * cnt; tpe_cp(dst + le * stride + off + j, src + i); }
+}
+template <typename R>
+__device__ __forceinline__ void tpe_zero(R* dst, int stride, int off, int cnt, int nv, int lane) {
+  const int total = nv * cnt;
+  for (int i = lane; i < total; i += 32) { const int le = i / cnt, j = i - le * cnt; dst[le * stride + off + j] = R(0); }
+}
+__host__ __device__ constexpr int tpe_lqr_stride_f(int n, int m) { return ((n + m) * (n + m) + (n + m) + n * (n + m) + n) | 1; }
+__host__ __device__ constexpr int tpe_lqr_stride_r(int n, int m) { return (m * n + m + n * (n + m) + n) | 1; }
+// reals of shared memory per warp: two sweep stages (the three rollout stages fit inside)
+__host__ __device__ constexpr int tpe_lqr_warp_reals(int n, int m) { return 2 * 32 * tpe_lqr_stride_f(n, m); }
+
+template <typename R, int N, int M, int TPB>
+__global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
+  constexpr int n = N, m = M, s = N + M, NC = N + 1 + M;
+  constexpr int SF = tpe_lqr_stride_f(N, M), SR = tpe_lqr_stride_r(N, M);
+  constexpr int oC = 0, oc = s * s, oF = s * s + s, of = s * s + s + n * s;      // sweep slot: C | c | F | f
+  constexpr int rK = 0, rk = m * n, rF = m * n + m, rf = m * n + m + n * s;      // rollout slot: K | k | F | f
+  static_assert(3 * SR <= 2 * SF, "three rollout stages must fit the two sweep stages");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = p.T;
+  const int lane = threadIdx.x & 31;
+  const int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31);                   // first element of this warp
+  if (e0 >= p.B) return;                                                          // whole warp (only __syncwarp below)
+  const int nv = p.B - e0 < 32 ? p.B - e0 : 32;                                   // elements of this warp
+  const bool valid = lane < nv;
+  const int ls = valid ? lane : nv - 1;                                           // padding lanes shadow the last element
+  const int e = e0 + ls;
+  const size_t tb = (size_t)p.B;
+  const bool masked = (p.flags & LQR_MASKED) != 0;
+  const bool save_fac = (p.flags & LQR_SAVE_FAC) != 0 && p.fac != nullptr;
+  const bool have_f = p.f != nullptr;
+  R* wsm = reinterpret_cast<R*>(smem_raw) + (size_t)(threadIdx.x >> 5) * tpe_lqr_warp_reals(N, M);
+
+  if (p.flags & LQR_DO_FACTOR) {
+    const R cs = p.c_scale;
+    auto issue = [&](int t, int slot) {
+      R* st = wsm + slot * 32 * SF;
+      const size_t i0 = (size_t)t * tb + e0;
+      tpe_stage(st, SF, oC, p.C + i0 * s * s, s * s, nv, lane);
+      if (p.c) {
+        tpe_stage(st, SF, oc, p.c + i0 * s, s, nv, lane);
+      } else {
+        if (p.cx) tpe_stage(st, SF, oc, p.cx + i0 * n, n, nv, lane); else tpe_zero(st, SF, oc, n, nv, lane);
+        if (p.cu) tpe_stage(st, SF, oc + n, p.cu + i0 * m, m, nv, lane); else tpe_zero(st, SF, oc + n, m, nv, lane);
+      }
+      if (t < T - 1) {
+        tpe_stage(st, SF, oF, p.F + i0 * n * s, n * s, nv, lane);
+        if (have_f) tpe_stage(st, SF, of, p.f + i0 * n, n, nv, lane);
+      }
+    };
+    issue(T - 1, 0);
+    cp_async_commit();
+    int slot = 0;
+    R V[n][n], v[n];
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t idx = (size_t)t * tb + e;
+      if (t > 0) issue(t - 1, slot ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      const R* my = wsm + slot * 32 * SF + ls * SF;
+      // Q starts as C_t, q as c_scale * c_t
+      R Q[s][s], q[s];
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+#pragma unroll
+        for (int j = 0; j < s; ++j) Q[i][j] = my[oC + i * s + j];
+        q[i] = cs * my[oc + i];
+      }
+      if (t < T - 1) {
+        R F[n][s];
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+          for (int j = 0; j < s; ++j) F[i][j] = my[oF + i * s + j];
+        // Q += F^T (V F), q += F^T (V f + v): one row of V F at a time (lqr_recursion.py:79-95)
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+          R Mk[s];
+#pragma unroll
+          for (int j = 0; j < s; ++j) {
+            R acc = R(0);
+#pragma unroll
+            for (int i = 0; i < n; ++i) acc += V[k][i] * F[i][j];
+            Mk[j] = acc;
+          }
+          R mvk = v[k];
+          if (have_f) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) mvk += V[k][i] * my[of + i];
+          }
+#pragma unroll
+          for (int i = 0; i < s; ++i) {
+#pragma unroll
+            for (int j = 0; j < s; ++j) Q[i][j] += F[k][i] * Mk[j];
+            q[i] += F[k][i] * mvk;
+          }
+        }
+      }
+      // H = Quu (masked: active rows / columns zeroed, +1e-8 on an active diagonal, active_constrained_lqr.py:112-126);
+      // X = [-Qux | -qu | I] -> after the solve [K | k | Quu^-1]
+      bool act[m];
+#pragma unroll
+      for (int i = 0; i < m; ++i) act[i] = masked && p.active[idx * m + i] != 0;
+      R H[m][m], X[m][NC];
+#pragma unroll
+      for (int i = 0; i < m; ++i) {
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+          R hv = Q[n + i][n + j];
+          if (act[i] || act[j]) hv = R(0);
+          if (act[i] && i == j) hv += R(1e-8);
+          H[i][j] = hv;
+        }
+#pragma unroll
+        for (int j = 0; j < n; ++j) X[i][j] = act[i] ? R(0) : -Q[n + i][j];
+        X[i][n] = act[i] ? R(0) : -q[n + i];
+#pragma unroll
+        for (int j = 0; j < m; ++j) X[i][n + 1 + j] = (i == j) ? R(1) : R(0);
+      }
+      tpe_solve<R, M, NC>(H, X);
+      if (valid) {
+        R* Kg = p.Ks + idx * m * n; R* kg = p.ks + idx * m;
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+#pragma unroll
+          for (int j = 0; j < n; ++j) Kg[i * n + j] = X[i][j];
+          kg[i] = X[i][n];
+        }
+        if (save_fac) {
+          R* fg = p.fac + idx * (m * m + n * m);
+#pragma unroll
+          for (int i = 0; i < m; ++i)
+#pragma unroll
+            for (int j = 0; j < m; ++j) fg[i * m + j] = X[i][n + 1 + j];
+#pragma unroll
+          for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int j = 0; j < m; ++j) fg[m * m + i * m + j] = Q[i][n + j];
+        }
+      }
+      if (t > 0) {
+        // P = [Qux | qu] + Quu [K | k] (unmasked Quu, Qux: Q6);  [V | v] = [Qxx | qx] + Qxu [K | k] + K^T P
+        R P[m][n + 1];
+#pragma unroll
+        for (int i = 0; i < m; ++i)
+#pragma unroll
+          for (int j = 0; j <= n; ++j) {
+            R a = (j < n) ? Q[n + i][j] : q[n + i];
+#pragma unroll
+            for (int l = 0; l < m; ++l) a += Q[n + i][n + l] * X[l][j];
+            P[i][j] = a;
+          }
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+          for (int j = 0; j <= n; ++j) {
+            R a = (j < n) ? Q[i][j] : q[i];
+            R b = R(0);
+#pragma unroll
+            for (int l = 0; l < m; ++l) { a += Q[i][n + l] * X[l][j]; b += X[l][i] * P[l][j]; }
+            if (j < n) V[i][j] = a + b; else v[i] = a + b;
+          }
+        if (p.Vsave && valid) {
+          R* Vg = p.Vsave + idx * (n * n + n);
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) Vg[i * n + j] = V[i][j];
+            Vg[n * n + i] = v[i];
+          }
+        }
+      }
+      __syncwarp();                                          // every lane is done with this stage before it is refilled
+      slot ^= 1;
+    }
+  }
+
+  if (p.flags & LQR_DO_ROLLOUT) {                            // lqr_recursion.py:160-200
+    // K_t, k_t were written by this warp's own lanes above (or by an earlier launch): make them visible to the copies
+    __threadfence_block();
+    __syncwarp();
+    auto issue = [&](int t, int slot) {
+      R* st = wsm + slot * 32 * SR;
+      const size_t i0 = (size_t)t * tb + e0;
+      tpe_stage(st, SR, rK, p.Ks + i0 * m * n, m * n, nv, lane);
+      tpe_stage(st, SR, rk, p.ks + i0 * m, m, nv, lane);
+      if (t < T - 1) {
+        tpe_stage(st, SR, rF, p.F + i0 * n * s, n * s, nv, lane);
+        if (have_f) tpe_stage(st, SR, rf, p.f + i0 * n, n, nv, lane);
+      }
+    };
+    issue(0, 0);
+    cp_async_commit();
+    if (T > 1) issue(1, 1);
+    cp_async_commit();
+    int slot = 0;
+    R x[s];
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = p.x0[(size_t)e * n + i];
+    for (int t = 0; t < T; ++t) {
+      const size_t idx = (size_t)t * tb + e;
+      if (t + 2 < T) issue(t + 2, slot >= 1 ? slot - 1 : 2);  // (slot + 2) % 3
+      cp_async_commit();
+      cp_async_wait<2>();
+      __syncwarp();
+      const R* my = wsm + slot * 32 * SR + ls * SR;
+#pragma unroll
+      for (int o = 0; o < m; ++o) {
+        R a0 = my[rk + o], a1 = R(0);                        // two interleaved accumulators
+#pragma unroll
+        for (int k = 0; k < n; ++k) { if (k & 1) a1 += my[rK + o * n + k] * x[k]; else a0 += my[rK + o * n + k] * x[k]; }
+        R uv = a0 + a1;
+        if (masked && p.active[idx * m + o]) uv = R(0);      // active_constrained_lqr.py:175
+        x[n + o] = uv;
+      }
+      if (valid) {
+        if (p.x) {
+#pragma unroll
+          for (int i = 0; i < n; ++i) p.x[idx * n + i] = x[i];
+        }
+        if (p.u) {
+#pragma unroll
+          for (int i = 0; i < m; ++i) p.u[idx * m + i] = x[n + i];
+        }
+        if (p.tau_out) {
+#pragma unroll
+          for (int i = 0; i < s; ++i) p.tau_out[idx * s + i] = x[i];
+        }
+      }
+      if (t < T - 1) {
+        R xn[n];
+#pragma unroll
+        for (int o = 0; o < n; ++o) {
+          R a0 = have_f ? my[rf + o] : R(0), a1 = R(0);
+#pragma unroll
+          for (int k = 0; k < s; ++k) { if (k & 1) a1 += my[rF + o * s + k] * x[k]; else a0 += my[rF + o * s + k] * x[k]; }
+          xn[o] = a0 + a1;
+        }
+#pragma unroll
+        for (int o = 0; o < n; ++o) x[o] = xn[o];
+      }
+      __syncwarp();
+      slot = slot == 2 ? 0 : slot + 1;
+    }
+  }
+}
+
+}  // namespace dmpc

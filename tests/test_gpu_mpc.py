@@ -186,8 +186,9 @@ def test_mpc_step_forward_random_vs_oracle(ctx, T, B, n, m, bound):
     assert rel_err(r["costs"], fo.costs) < 1e-10
 
 
-def test_lqr_active_vs_oracle(ctx):
-    T, B, n, m = 12, 21, 6, 3
+@pytest.mark.parametrize("T,B,n,m", [(12, 21, 6, 3), (16, 70, 4, 2), (20, 35, 3, 1), (9, 5, 2, 1)])
+def test_lqr_active_vs_oracle(ctx, T, B, n, m):
+    """(6,3): group kernel; (4,2), (3,1), (2,1): thread-per-element kernel (lqr_tpe_kernel.cuh), masked rows included."""
     rs = np.random.RandomState(5)
     C, c = psd_cost(rs, T, B, n + m)
     F = stable_dynamics(rs, T, B, n, m)
