@@ -7,9 +7,8 @@
 // memory, with seven group barriers and a generic LU per time step; at s = 6 a Riccati step is ~700 flops, and the group
 // kernel spends ~7900 cycles on it (profiles/r2/r2y_bench_c2.json: 0.201 ms for T = 50) - dependent-chain latency, not
 // bandwidth (7 % of HBM).  A thread that owns the element needs no barrier, no shared memory, and its m <= 2 elimination
-// is a handful of FMAs.  Same contract as lqr_solve_kernel (LqrParams, every flag), same operation order where rounding
-// could matter to a caller comparing runs (pivoting: first maximum wins; multipliers through the pivot's reciprocal;
-// back substitution by division).
+// is a handful of FMAs.  Same contract as lqr_solve_kernel (LqrParams, every flag); pivoting as there (first maximum
+// wins), the pivots enter through their reciprocals.
 #pragma once
 #include "lqr_kernels.cuh"
 
@@ -25,37 +24,46 @@ __device__ __forceinline__ void tpe_solve(R (&H)[M][M], R (&X)[M][NC]) {
 #pragma unroll
       for (int j = 0; j < NC; ++j) { const R t = X[0][j]; X[0][j] = X[1][j]; X[1][j] = t; }
     }
-    const R l = H[1][0] * (R(1) / H[0][0]);
-    H[1][1] -= l * H[0][1];
-#pragma unroll
-    for (int j = 0; j < NC; ++j) X[1][j] -= l * X[0][j];
+    // two reciprocals per step instead of a division per column and row: the divisions (and the branch around each
+    // one's slow path) were a third of the step's dependent chain
+    const R r0 = R(1) / H[0][0];
+    const R l = H[1][0] * r0;
+    const R r1 = R(1) / (H[1][1] - l * H[0][1]);
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
-      X[1][j] = div_z(X[1][j], H[1][1]);
-      X[0][j] = div_z(X[0][j] - H[0][1] * X[1][j], H[0][0]);
+      X[1][j] = (X[1][j] - l * X[0][j]) * r1;
+      X[0][j] = (X[0][j] - H[0][1] * X[1][j]) * r0;
     }
   } else {
     static_assert(M == 1, "tpe_solve: m <= 2");
+    const R r0 = R(1) / H[0][0];                             // lqr_recursion.py:112-115 takes the scalar reciprocal too
 #pragma unroll
-    for (int j = 0; j < NC; ++j) X[0][j] = div_z(X[0][j], H[0][0]);
+    for (int j = 0; j < NC; ++j) X[0][j] *= r0;
   }
 }
 
-// Operand staging.  Elements e0 .. e0+31 of one time step are CONTIGUOUS in the reference layout ([T][B][...]), but a
-// thread that loads its own element directly touches a different 128-byte line than its neighbour: every LDG is 32
-// separate L1 requests and the step is bound by the load pipe and by exposed DRAM latency (measured: the first version of
-// this kernel, direct loads + L2 prefetch, 0.179 ms against the group kernel's 0.201 ms at config 2).  So the WARP copies
-// the step's operands of its 32 elements with coalesced cp.async into a ring of shared-memory stages (one slot per
-// element, odd stride: conflict-free reads), one step ahead in the Riccati sweep and two in the rollout.
 template <typename R>
 __device__ __forceinline__ void tpe_cp(R* sdst, const R* g) {
   if (sizeof(R) == 8) cp_async8(sdst, g); else cp_async4(sdst, g);
 }
-// `cnt` reals per element for `nv` consecutive elements -> slot[le * stride + off + j]
-template <typename R>
-__device__ __forceinline__ void tpe_stage(R* dst, int stride, int off, const R* src, int cnt, int nv, int lane) {
-  const int total = nv * cnt;
-  for (int i = lane; i < total; i += 32) { const int le = i / cnt, j = i - le * cnt; tpe_cp(dst + le * stride + off + j, src + i); }
+// CNT reals per element for `nv` consecutive elements -> slot[le * stride + off + j].  Full warps (nv == 32) take the
+// unrolled path: the (element, item) pair of a lane's i-th copy advances by compile-time constants, no division.
+template <int CNT, typename R>
+__device__ __forceinline__ void tpe_stage(R* dst, int stride, int off, const R* src, int nv, int lane) {
+  if (nv == 32) {
+    constexpr int Q32 = 32 / CNT, R32 = 32 % CNT;
+    int j = lane % CNT;
+    int d = (lane / CNT) * stride + off + j;
+#pragma unroll
+    for (int it = 0; it < CNT; ++it) {
+      tpe_cp(dst + d, src + lane + 32 * it);
+      j += R32; d += Q32 * stride + R32;
+      if (j >= CNT) { j -= CNT; d += stride - CNT; }
+    }
+  } else {
+    const int total = nv * CNT;
+    for (int i = lane; i < total; i += 32) { const int le = i / CNT, j = i - le * CNT; tpe_cp(dst + le * stride + off + j, src + i); }
+  }
 }
 template <typename R>
 __device__ __forceinline__ void tpe_zero(R* dst, int stride, int off, int cnt, int nv, int lane) {
@@ -94,16 +102,16 @@ __global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
     auto issue = [&](int t, int slot) {
       R* st = wsm + slot * 32 * SF;
       const size_t i0 = (size_t)t * tb + e0;
-      tpe_stage(st, SF, oC, p.C + i0 * s * s, s * s, nv, lane);
+      tpe_stage<s * s>(st, SF, oC, p.C + i0 * s * s, nv, lane);
       if (p.c) {
-        tpe_stage(st, SF, oc, p.c + i0 * s, s, nv, lane);
+        tpe_stage<s>(st, SF, oc, p.c + i0 * s, nv, lane);
       } else {
-        if (p.cx) tpe_stage(st, SF, oc, p.cx + i0 * n, n, nv, lane); else tpe_zero(st, SF, oc, n, nv, lane);
-        if (p.cu) tpe_stage(st, SF, oc + n, p.cu + i0 * m, m, nv, lane); else tpe_zero(st, SF, oc + n, m, nv, lane);
+        if (p.cx) tpe_stage<n>(st, SF, oc, p.cx + i0 * n, nv, lane); else tpe_zero(st, SF, oc, n, nv, lane);
+        if (p.cu) tpe_stage<m>(st, SF, oc + n, p.cu + i0 * m, nv, lane); else tpe_zero(st, SF, oc + n, m, nv, lane);
       }
       if (t < T - 1) {
-        tpe_stage(st, SF, oF, p.F + i0 * n * s, n * s, nv, lane);
-        if (have_f) tpe_stage(st, SF, of, p.f + i0 * n, n, nv, lane);
+        tpe_stage<n * s>(st, SF, oF, p.F + i0 * n * s, nv, lane);
+        if (have_f) tpe_stage<n>(st, SF, of, p.f + i0 * n, nv, lane);
       }
     };
     issue(T - 1, 0);
@@ -241,11 +249,11 @@ __global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
     auto issue = [&](int t, int slot) {
       R* st = wsm + slot * 32 * SR;
       const size_t i0 = (size_t)t * tb + e0;
-      tpe_stage(st, SR, rK, p.Ks + i0 * m * n, m * n, nv, lane);
-      tpe_stage(st, SR, rk, p.ks + i0 * m, m, nv, lane);
+      tpe_stage<m * n>(st, SR, rK, p.Ks + i0 * m * n, nv, lane);
+      tpe_stage<m>(st, SR, rk, p.ks + i0 * m, nv, lane);
       if (t < T - 1) {
-        tpe_stage(st, SR, rF, p.F + i0 * n * s, n * s, nv, lane);
-        if (have_f) tpe_stage(st, SR, rf, p.f + i0 * n, n, nv, lane);
+        tpe_stage<n * s>(st, SR, rF, p.F + i0 * n * s, nv, lane);
+        if (have_f) tpe_stage<n>(st, SR, rf, p.f + i0 * n, nv, lane);
       }
     };
     issue(0, 0);
