@@ -605,7 +605,8 @@ def run_b200(args):
         peak, peak_src = measured_peaks()
         traffic = ncu_traffic()
         dmma = dmma_shape(n, m)
-        fwd_name = "lqr_factor_dmma_warp_kernel" if dmma else "lqr_solve_kernel"
+        tpe = (n, m) in ((2, 1), (3, 1), (4, 2)) and os.environ.get("DMPC_LQR_GROUP", "0") != "1"   # csrc/lqr_launch.cu
+        fwd_name = "lqr_factor_dmma_warp_kernel" if dmma else ("lqr_tpe_kernel" if tpe else "lqr_solve_kernel")
         s_ = n + m
         dtau_b = 8 * (2 * (T - 1) * n * s_ + T * (m * m + n * m) + T * m * n + 2 * T * s_)        # F twice, factors, K, grads, d-tau
         fused_adj = dmma          # n=32/m=8: two-sweep adjoint on the saved V_t, v_t (csrc/lqr_adjoint_fused.cuh)

@@ -104,6 +104,21 @@ int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
 template <typename R>
 int launch_lqr_dtau(const DtauParams<R>& p, cudaStream_t st, long long* nl) {
   const ShapeInfo si = pick_shape_impl(p.n, p.m);
+  if (lqr_tpe_enabled()) {                                    // s <= 6: thread per element (lqr_tpe_kernel.cuh)
+    const int tpb = p.B >= 148 * 64 * 2 ? 64 : 32;
+    const int grid = (p.B + tpb - 1) / tpb;
+#define X(N_, M_)                                                                                            \
+    if (p.n == N_ && p.m == M_) {                                                                            \
+      auto k = lqr_dtau_tpe_kernel<R, N_, M_, 64>;                                                           \
+      const size_t sm = (size_t)(tpb / 32) * tpe_dtau_warp_reals(N_, M_) * sizeof(R);                        \
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA; \
+      k<<<grid, tpb, sm, st>>>(p);                                                                           \
+      if (nl) ++*nl;                                                                                         \
+      return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;                                    \
+    }
+    X(2, 1) X(3, 1) X(4, 2)
+#undef X
+  }
   const DtauLayout L = dtau_layout<R>(p.n, p.m);
   const size_t sb = (size_t)L.stride * sizeof(R);
 #define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) return do_launch(lqr_dtau_kernel<R, N_, M_, (G_ > 32 ? 64 : G_)>, p, (G_ > 32 ? 64 : G_), sb, p.B, st, nl);

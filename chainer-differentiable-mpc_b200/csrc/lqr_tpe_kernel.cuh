@@ -312,4 +312,161 @@ __global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
   }
 }
 
+// dot_rot (common.cuh) on compile-time sizes: same rotated start, same two interleaved accumulators, fully unrolled so
+// that register arrays stay in registers
+template <int K, int ROT, typename R, typename A, typename B>
+__device__ __forceinline__ R tpe_dot_rot(const A& row, const B& vec, R init) {
+  R a0 = init, a1 = R(0);
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const int k = (ROT % K + i) % K;
+    if (i & 1) a1 += row(k) * vec(k); else a0 += row(k) * vec(k);
+  }
+  return a0 + a1;
+}
+
+// The second LQR solve of DiffLqr.backward with the saved factors (lqr_dtau_kernel, non-fused form; reference
+// lqr/differentiable_lqr.py:106-112) for s <= 6, one thread per element.  The work per step is two tiny mat-vecs: the
+// group kernel's 1 us per step (config 2: 0.100 ms for 2 x 50 steps) is its two-stage operand pipeline against DRAM
+// latency, so the ring here is three stages deep (two steps ahead) in both sweeps.  dc carries k'_t in its control rows
+// between the sweeps exactly as in lqr_dtau_kernel.
+__host__ __device__ constexpr int tpe_dtau_stride(int n, int m) { return (n * (n + m) + m * m + n * m + n + m) | 1; }
+__host__ __device__ constexpr int tpe_dtau_warp_reals(int n, int m) { return 3 * 32 * tpe_dtau_stride(n, m); }
+
+template <int O, int M, typename R, typename QV>
+__device__ __forceinline__ void tpe_dtau_kp(const R* fac, const QV& qu, R (&kp)[M]) {
+  if constexpr (O < M) {
+    kp[O] = -tpe_dot_rot<M, O, R>([&](int k) { return fac[O * M + k]; }, qu, R(0));
+    tpe_dtau_kp<O + 1, M, R>(fac, qu, kp);
+  }
+}
+template <int O, int N, int M, typename R>
+__device__ __forceinline__ void tpe_dtau_vp(const R* qxu, const R (&kp)[M], const R (&q)[N + M], R (&vp)[N]) {
+  if constexpr (O < N) {
+    vp[O] = tpe_dot_rot<M, O, R>([&](int k) { return qxu[O * M + k]; }, [&](int k) { return kp[k]; }, q[O]);
+    tpe_dtau_vp<O + 1, N, M, R>(qxu, kp, q, vp);
+  }
+}
+template <int O, int N, int M, typename R>
+__device__ __forceinline__ void tpe_dtau_du(const R* Kt, const R (&kn)[M], R (&dx)[N + M]) {
+  if constexpr (O < M) {
+    dx[N + O] = tpe_dot_rot<N, O, R>([&](int k) { return Kt[O * N + k]; }, [&](int k) { return dx[k]; }, kn[O]);
+    tpe_dtau_du<O + 1, N, M, R>(Kt, kn, dx);
+  }
+}
+template <int O, int N, int M, typename R>
+__device__ __forceinline__ void tpe_dtau_dx(const R* Ft, const R (&dx)[N + M], R (&xn)[N]) {
+  if constexpr (O < N) {
+    xn[O] = tpe_dot_rot<N + M, O, R>([&](int k) { return Ft[O * (N + M) + k]; }, [&](int k) { return dx[k]; }, R(0));
+    tpe_dtau_dx<O + 1, N, M, R>(Ft, dx, xn);
+  }
+}
+
+template <typename R, int N, int M, int TPB>
+__global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p) {
+  constexpr int n = N, m = M, s = N + M, fsz = M * M + N * M;
+  constexpr int SD = tpe_dtau_stride(N, M);
+  constexpr int oF = 0, oA = n * s, ogx = n * s + fsz, ogu = n * s + fsz + n;      // sweep 1 slot: F | Quu^-1 | Qxu | gx | gu
+  constexpr int oK = n * s;                                                        // sweep 2 slot: F | K
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = p.T;
+  const int lane = threadIdx.x & 31;
+  const int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  if (e0 >= p.B) return;
+  const int nv = p.B - e0 < 32 ? p.B - e0 : 32;
+  const bool valid = lane < nv;
+  const int ls = valid ? lane : nv - 1;
+  const int e = e0 + ls;
+  const size_t tb = (size_t)p.B;
+  R* wsm = reinterpret_cast<R*>(smem_raw) + (size_t)(threadIdx.x >> 5) * tpe_dtau_warp_reals(N, M);
+
+  // ---- sweep 1 (t = T-1 .. 0): q = g_t + F_t^T v'_{t+1};  k'_t = -Quu^-1 q_u;  v'_t = q_x + Qxu k'_t
+  {
+    auto issue = [&](int t, int slot) {
+      R* st = wsm + slot * 32 * SD;
+      const size_t i0 = (size_t)t * tb + e0;
+      if (t < T - 1) tpe_stage<n * s>(st, SD, oF, p.F + i0 * n * s, nv, lane);
+      tpe_stage<fsz>(st, SD, oA, p.fac + i0 * fsz, nv, lane);
+      tpe_stage<n>(st, SD, ogx, p.gx + i0 * n, nv, lane);
+      tpe_stage<m>(st, SD, ogu, p.gu + i0 * m, nv, lane);
+    };
+    issue(T - 1, 0);
+    cp_async_commit();
+    if (T > 1) issue(T - 2, 1);
+    cp_async_commit();
+    int slot = 0;
+    R vp[n];
+    for (int t = T - 1; t >= 0; --t) {
+      if (t >= 2) issue(t - 2, slot >= 1 ? slot - 1 : 2);
+      cp_async_commit();
+      cp_async_wait<2>();
+      __syncwarp();
+      const R* my = wsm + slot * 32 * SD + ls * SD;
+      R q[s];
+#pragma unroll
+      for (int o = 0; o < s; ++o) {
+        R a0 = (o < n) ? my[ogx + o] : my[ogu + o - n], a1 = R(0);
+        if (t < T - 1) {
+#pragma unroll
+          for (int k = 0; k < n; ++k) { if (k & 1) a1 += my[oF + k * s + o] * vp[k]; else a0 += my[oF + k * s + o] * vp[k]; }
+        }
+        q[o] = a0 + a1;
+      }
+      R kp[m];
+      tpe_dtau_kp<0, M, R>(my + oA, [&](int k) { return q[n + k]; }, kp);
+      tpe_dtau_vp<0, N, M, R>(my + oA + m * m, kp, q, vp);
+      if (valid) {
+#pragma unroll
+        for (int o = 0; o < m; ++o) p.dc[((size_t)t * tb + e) * s + n + o] = kp[o];
+      }
+      __syncwarp();
+      slot = slot == 2 ? 0 : slot + 1;
+    }
+  }
+  // ---- sweep 2 (t = 0 .. T-1): du_t = K_t dx_t + k'_t;  dx_{t+1} = F_t [dx_t; du_t];  dc[t] <- [dx_t; du_t]
+  {
+    auto issue = [&](int t, int slot) {
+      R* st = wsm + slot * 32 * SD;
+      const size_t i0 = (size_t)t * tb + e0;
+      if (t < T - 1) tpe_stage<n * s>(st, SD, oF, p.F + i0 * n * s, nv, lane);
+      tpe_stage<m * n>(st, SD, oK, p.Ks + i0 * m * n, nv, lane);
+    };
+    issue(0, 0);
+    cp_async_commit();
+    if (T > 1) issue(1, 1);
+    cp_async_commit();
+    int slot = 0;
+    R dx[s], kn[m];
+#pragma unroll
+    for (int o = 0; o < n; ++o) dx[o] = R(0);
+#pragma unroll
+    for (int o = 0; o < m; ++o) kn[o] = p.dc[(size_t)e * s + n + o];               // this thread's own k'_0 (written above)
+    for (int t = 0; t < T; ++t) {
+      const size_t idx = (size_t)t * tb + e;
+      if (t + 2 < T) issue(t + 2, slot >= 1 ? slot - 1 : 2);
+      cp_async_commit();
+      cp_async_wait<2>();
+      __syncwarp();
+      const R* my = wsm + slot * 32 * SD + ls * SD;
+      tpe_dtau_du<0, N, M, R>(my + oK, kn, dx);
+      if (t + 1 < T) {                                                             // k'_{t+1}: requested a step ahead
+#pragma unroll
+        for (int o = 0; o < m; ++o) kn[o] = p.dc[(idx + tb) * s + n + o];
+      }
+      if (valid) {
+#pragma unroll
+        for (int o = 0; o < s; ++o) p.dc[idx * s + o] = dx[o];
+      }
+      if (t < T - 1) {
+        R xn[n];
+        tpe_dtau_dx<0, N, M, R>(my + oF, dx, xn);
+#pragma unroll
+        for (int o = 0; o < n; ++o) dx[o] = xn[o];
+      }
+      __syncwarp();
+      slot = slot == 2 ? 0 : slot + 1;
+    }
+  }
+}
+
 }  // namespace dmpc
