@@ -76,8 +76,8 @@ int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
     const int grid = (p.B + tpb - 1) / tpb;
 #define X(N_, M_)                                                                                            \
     if (p.n == N_ && p.m == M_) {                                                                            \
-      auto k = lqr_tpe_kernel<R, N_, M_, 64>;                                                                \
-      const size_t sm = (size_t)(tpb / 32) * tpe_lqr_warp_reals(N_, M_) * sizeof(R);                         \
+      auto k = lqr_tpe_kernel<R, N_, M_, 64, 2, 3>;                                                          \
+      const size_t sm = (size_t)(tpb / 32) * tpe_lqr_warp_reals(N_, M_, 2, 3) * sizeof(R);                   \
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA; \
       k<<<grid, tpb, sm, st>>>(p);                                                                           \
       if (nl) ++*nl;                                                                                         \
@@ -109,8 +109,8 @@ int launch_lqr_dtau(const DtauParams<R>& p, cudaStream_t st, long long* nl) {
     const int grid = (p.B + tpb - 1) / tpb;
 #define X(N_, M_)                                                                                            \
     if (p.n == N_ && p.m == M_) {                                                                            \
-      auto k = lqr_dtau_tpe_kernel<R, N_, M_, 64>;                                                           \
-      const size_t sm = (size_t)(tpb / 32) * tpe_dtau_warp_reals(N_, M_) * sizeof(R);                        \
+      auto k = lqr_dtau_tpe_kernel<R, N_, M_, 64, 3>;                                                        \
+      const size_t sm = (size_t)(tpb / 32) * tpe_dtau_warp_reals(N_, M_, 3) * sizeof(R);                     \
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA; \
       k<<<grid, tpb, sm, st>>>(p);                                                                           \
       if (nl) ++*nl;                                                                                         \

@@ -72,16 +72,22 @@ __device__ __forceinline__ void tpe_zero(R* dst, int stride, int off, int cnt, i
 }
 __host__ __device__ constexpr int tpe_lqr_stride_f(int n, int m) { return ((n + m) * (n + m) + (n + m) + n * (n + m) + n) | 1; }
 __host__ __device__ constexpr int tpe_lqr_stride_r(int n, int m) { return (m * n + m + n * (n + m) + n) | 1; }
-// reals of shared memory per warp: two sweep stages (the three rollout stages fit inside)
-__host__ __device__ constexpr int tpe_lqr_warp_reals(int n, int m) { return 2 * 32 * tpe_lqr_stride_f(n, m); }
+// reals of shared memory per warp
+// ring depths: DS stages in the Riccati sweep (DS - 1 steps ahead), DR in the rollout; shipped: 2 / 3, and 3 for the
+// adjoint's solve below.  Deeper rings (4 / 8 / 8, for batches that leave each SM a single warp) were measured at config 2
+// and are slower: forward 0.165 against 0.143 ms, adjoint solve 0.096 against 0.079 ms (gpurun_out r2al vs r2ak) - the
+// longer prologue and the extra address arithmetic cost more than the exposed latency they remove.
+__host__ __device__ constexpr int tpe_lqr_warp_reals(int n, int m, int ds, int dr) {
+  return 32 * (ds * tpe_lqr_stride_f(n, m) > dr * tpe_lqr_stride_r(n, m) ? ds * tpe_lqr_stride_f(n, m) : dr * tpe_lqr_stride_r(n, m));
+}
 
-template <typename R, int N, int M, int TPB>
+template <typename R, int N, int M, int TPB, int DS, int DR>
 __global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
   constexpr int n = N, m = M, s = N + M, NC = N + 1 + M;
   constexpr int SF = tpe_lqr_stride_f(N, M), SR = tpe_lqr_stride_r(N, M);
   constexpr int oC = 0, oc = s * s, oF = s * s + s, of = s * s + s + n * s;      // sweep slot: C | c | F | f
   constexpr int rK = 0, rk = m * n, rF = m * n + m, rf = m * n + m + n * s;      // rollout slot: K | k | F | f
-  static_assert(3 * SR <= 2 * SF, "three rollout stages must fit the two sweep stages");
+  static_assert(DS >= 2 && DR >= 2, "ring depths");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = p.T;
   const int lane = threadIdx.x & 31;
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
   const bool masked = (p.flags & LQR_MASKED) != 0;
   const bool save_fac = (p.flags & LQR_SAVE_FAC) != 0 && p.fac != nullptr;
   const bool have_f = p.f != nullptr;
-  R* wsm = reinterpret_cast<R*>(smem_raw) + (size_t)(threadIdx.x >> 5) * tpe_lqr_warp_reals(N, M);
+  R* wsm = reinterpret_cast<R*>(smem_raw) + (size_t)(threadIdx.x >> 5) * tpe_lqr_warp_reals(N, M, DS, DR);
 
   if (p.flags & LQR_DO_FACTOR) {
     const R cs = p.c_scale;
@@ -114,15 +120,18 @@ __global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
         if (have_f) tpe_stage<n>(st, SF, of, p.f + i0 * n, nv, lane);
       }
     };
-    issue(T - 1, 0);
-    cp_async_commit();
+#pragma unroll
+    for (int k = 0; k < DS - 1; ++k) {                       // stage of step t lives in slot (T - 1 - t) % DS
+      if (T - 1 - k >= 0) issue(T - 1 - k, k);
+      cp_async_commit();
+    }
     int slot = 0;
     R V[n][n], v[n];
     for (int t = T - 1; t >= 0; --t) {
       const size_t idx = (size_t)t * tb + e;
-      if (t > 0) issue(t - 1, slot ^ 1);
+      if (t - (DS - 1) >= 0) issue(t - (DS - 1), slot == 0 ? DS - 1 : slot - 1);
       cp_async_commit();
-      cp_async_wait<1>();
+      cp_async_wait<DS - 1>();
       __syncwarp();
       const R* my = wsm + slot * 32 * SF + ls * SF;
       // Q starts as C_t, q as c_scale * c_t
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
         }
       }
       __syncwarp();                                          // every lane is done with this stage before it is refilled
-      slot ^= 1;
+      slot = slot == DS - 1 ? 0 : slot + 1;
     }
   }
 
@@ -256,19 +265,20 @@ __global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
         if (have_f) tpe_stage<n>(st, SR, rf, p.f + i0 * n, nv, lane);
       }
     };
-    issue(0, 0);
-    cp_async_commit();
-    if (T > 1) issue(1, 1);
-    cp_async_commit();
+#pragma unroll
+    for (int k = 0; k < DR - 1; ++k) {                       // stage of step t lives in slot t % DR
+      if (k < T) issue(k, k);
+      cp_async_commit();
+    }
     int slot = 0;
     R x[s];
 #pragma unroll
     for (int i = 0; i < n; ++i) x[i] = p.x0[(size_t)e * n + i];
     for (int t = 0; t < T; ++t) {
       const size_t idx = (size_t)t * tb + e;
-      if (t + 2 < T) issue(t + 2, slot >= 1 ? slot - 1 : 2);  // (slot + 2) % 3
+      if (t + DR - 1 < T) issue(t + DR - 1, slot == 0 ? DR - 1 : slot - 1);
       cp_async_commit();
-      cp_async_wait<2>();
+      cp_async_wait<DR - 1>();
       __syncwarp();
       const R* my = wsm + slot * 32 * SR + ls * SR;
 #pragma unroll
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
         for (int o = 0; o < n; ++o) x[o] = xn[o];
       }
       __syncwarp();
-      slot = slot == 2 ? 0 : slot + 1;
+      slot = slot == DR - 1 ? 0 : slot + 1;
     }
   }
 }
@@ -328,10 +338,10 @@ __device__ __forceinline__ R tpe_dot_rot(const A& row, const B& vec, R init) {
 // The second LQR solve of DiffLqr.backward with the saved factors (lqr_dtau_kernel, non-fused form; reference
 // lqr/differentiable_lqr.py:106-112) for s <= 6, one thread per element.  The work per step is two tiny mat-vecs: the
 // group kernel's 1 us per step (config 2: 0.100 ms for 2 x 50 steps) is its two-stage operand pipeline against DRAM
-// latency, so the ring here is three stages deep (two steps ahead) in both sweeps.  dc carries k'_t in its control rows
+// latency, so the ring here is at least three stages deep (DD - 1 steps ahead) in both sweeps.  dc carries k'_t in its control rows
 // between the sweeps exactly as in lqr_dtau_kernel.
 __host__ __device__ constexpr int tpe_dtau_stride(int n, int m) { return (n * (n + m) + m * m + n * m + n + m) | 1; }
-__host__ __device__ constexpr int tpe_dtau_warp_reals(int n, int m) { return 3 * 32 * tpe_dtau_stride(n, m); }
+__host__ __device__ constexpr int tpe_dtau_warp_reals(int n, int m, int dd) { return dd * 32 * tpe_dtau_stride(n, m); }
 
 template <int O, int M, typename R, typename QV>
 __device__ __forceinline__ void tpe_dtau_kp(const R* fac, const QV& qu, R (&kp)[M]) {
@@ -362,7 +372,7 @@ __device__ __forceinline__ void tpe_dtau_dx(const R* Ft, const R (&dx)[N + M], R
   }
 }
 
-template <typename R, int N, int M, int TPB>
+template <typename R, int N, int M, int TPB, int DD>
 __global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p) {
   constexpr int n = N, m = M, s = N + M, fsz = M * M + N * M;
   constexpr int SD = tpe_dtau_stride(N, M);
@@ -378,7 +388,7 @@ __global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p) {
   const int ls = valid ? lane : nv - 1;
   const int e = e0 + ls;
   const size_t tb = (size_t)p.B;
-  R* wsm = reinterpret_cast<R*>(smem_raw) + (size_t)(threadIdx.x >> 5) * tpe_dtau_warp_reals(N, M);
+  R* wsm = reinterpret_cast<R*>(smem_raw) + (size_t)(threadIdx.x >> 5) * tpe_dtau_warp_reals(N, M, DD);
 
   // ---- sweep 1 (t = T-1 .. 0): q = g_t + F_t^T v'_{t+1};  k'_t = -Quu^-1 q_u;  v'_t = q_x + Qxu k'_t
   {
@@ -390,16 +400,17 @@ __global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p) {
       tpe_stage<n>(st, SD, ogx, p.gx + i0 * n, nv, lane);
       tpe_stage<m>(st, SD, ogu, p.gu + i0 * m, nv, lane);
     };
-    issue(T - 1, 0);
-    cp_async_commit();
-    if (T > 1) issue(T - 2, 1);
-    cp_async_commit();
+#pragma unroll
+    for (int k = 0; k < DD - 1; ++k) {
+      if (T - 1 - k >= 0) issue(T - 1 - k, k);
+      cp_async_commit();
+    }
     int slot = 0;
     R vp[n];
     for (int t = T - 1; t >= 0; --t) {
-      if (t >= 2) issue(t - 2, slot >= 1 ? slot - 1 : 2);
+      if (t - (DD - 1) >= 0) issue(t - (DD - 1), slot == 0 ? DD - 1 : slot - 1);
       cp_async_commit();
-      cp_async_wait<2>();
+      cp_async_wait<DD - 1>();
       __syncwarp();
       const R* my = wsm + slot * 32 * SD + ls * SD;
       R q[s];
@@ -420,7 +431,7 @@ __global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p) {
         for (int o = 0; o < m; ++o) p.dc[((size_t)t * tb + e) * s + n + o] = kp[o];
       }
       __syncwarp();
-      slot = slot == 2 ? 0 : slot + 1;
+      slot = slot == DD - 1 ? 0 : slot + 1;
     }
   }
   // ---- sweep 2 (t = 0 .. T-1): du_t = K_t dx_t + k'_t;  dx_{t+1} = F_t [dx_t; du_t];  dc[t] <- [dx_t; du_t]
@@ -431,10 +442,11 @@ __global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p) {
       if (t < T - 1) tpe_stage<n * s>(st, SD, oF, p.F + i0 * n * s, nv, lane);
       tpe_stage<m * n>(st, SD, oK, p.Ks + i0 * m * n, nv, lane);
     };
-    issue(0, 0);
-    cp_async_commit();
-    if (T > 1) issue(1, 1);
-    cp_async_commit();
+#pragma unroll
+    for (int k = 0; k < DD - 1; ++k) {
+      if (k < T) issue(k, k);
+      cp_async_commit();
+    }
     int slot = 0;
     R dx[s], kn[m];
 #pragma unroll
@@ -443,9 +455,9 @@ __global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p) {
     for (int o = 0; o < m; ++o) kn[o] = p.dc[(size_t)e * s + n + o];               // this thread's own k'_0 (written above)
     for (int t = 0; t < T; ++t) {
       const size_t idx = (size_t)t * tb + e;
-      if (t + 2 < T) issue(t + 2, slot >= 1 ? slot - 1 : 2);
+      if (t + DD - 1 < T) issue(t + DD - 1, slot == 0 ? DD - 1 : slot - 1);
       cp_async_commit();
-      cp_async_wait<2>();
+      cp_async_wait<DD - 1>();
       __syncwarp();
       const R* my = wsm + slot * 32 * SD + ls * SD;
       tpe_dtau_du<0, N, M, R>(my + oK, kn, dx);
@@ -464,7 +476,7 @@ __global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p) {
         for (int o = 0; o < n; ++o) dx[o] = xn[o];
       }
       __syncwarp();
-      slot = slot == 2 ? 0 : slot + 1;
+      slot = slot == DD - 1 ? 0 : slot + 1;
     }
   }
 }

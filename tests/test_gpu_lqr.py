@@ -108,6 +108,29 @@ def test_lqr_adjoint_random(ctx, T, B, n, m, with_f, dtype, strict):
         assert rel_err(a, b) < TOL[dtype] * (10 if dtype == np.float32 else 1), k
 
 
+@pytest.mark.parametrize("B,n,m", [(9601, 4, 2), (19003, 3, 1)])
+def test_tpe_kernels_other_launch_geometries(ctx, B, n, m):
+    """lqr_tpe_kernel / lqr_dtau_tpe_kernel (s <= 6) pick their operand-ring depth and CTA size from the batch: every other
+    test runs the deep-ring, one-warp-CTA form (B <= 9472).  9601 -> shallow rings, 32-thread CTAs; 19003 -> shallow rings,
+    64-thread CTAs; both with a ragged last warp.  Elements are independent, so the oracle runs on two slices."""
+    T = 6
+    pr = lqr_problem(B + n, T, B, n, m, with_f=True)
+    rs = np.random.RandomState(4)
+    gx, gu = rs.randn(T, B, n), rs.randn(T, B, m)
+    r = run_solve(ctx, pr)
+    out = run_adjoint(ctx, r, gx, gu)
+    got = {k: r[k].download() for k in ("x", "u", "Ks", "ks")}
+    for sl in (slice(0, 40), slice(B - 45, B)):
+        ox, ou, oK, ok = olqr.lqr_solve(pr["x0"][sl], pr["C"][:, sl], pr["c"][:, sl], pr["F"][:, sl], pr["f"][:, sl], n, m)
+        for a, b, k in ((got["x"], ox, "x"), (got["u"], ou, "u"), (got["Ks"], oK, "Ks"), (got["ks"], ok, "ks")):
+            assert rel_err(a[:, sl], b) < 1e-10, k
+        want = olqr.difflqr_backward(pr["x0"][sl], pr["C"][:, sl], pr["c"][:, sl], pr["F"][:, sl], ox, ou, gx[:, sl], gu[:, sl],
+                                     n, m, quirk_dC=True, quirk_df=True)
+        assert rel_err(out[0][sl], want[0]) < 1e-10, "dx0"
+        for a, b, k in zip(out[1:], want[1:], ("dC", "dc", "dF", "df")):
+            assert rel_err(a[:, sl], b) < 1e-10, k
+
+
 def test_factor_then_rollout_split(ctx):
     """LqrRecursion.backward() then .forward(Ks, ks) as two calls == solve_recursion()."""
     pr = lqr_problem(5, 15, 40, 4, 2)
