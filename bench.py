@@ -610,7 +610,7 @@ def run_b200(args):
         s_ = n + m
         dtau_b = 8 * (2 * (T - 1) * n * s_ + T * (m * m + n * m) + T * m * n + 2 * T * s_)        # F twice, factors, K, grads, d-tau
         fused_adj = dmma          # n=32/m=8: two-sweep adjoint on the saved V_t, v_t (csrc/lqr_adjoint_fused.cuh)
-        k1 = "lqr_dtau_kernel<FUSED>" if fused_adj else "lqr_dtau_kernel"
+        k1 = "lqr_dtau_kernel<FUSED>" if fused_adj else ("lqr_dtau_tpe_kernel" if tpe else "lqr_dtau_kernel")
         k2 = "adjoint_fused_kernel" if fused_adj else "adjoint_out_kernel"
         kernels = {
             fwd_name: {"ms": kt["forward"], "launches_per_step": 1, "algorithmic_bytes": Bc * fwd_b,
@@ -627,7 +627,7 @@ def run_b200(args):
                           "(lambda comes from the saved V_t, v_t), so hbm_frac on algorithmic bytes can exceed 1 while the measured "
                           "DRAM traffic stays below the peak" if fused_adj else "")}}
         red_name = ("lqr_dtau_kernel<FUSED>+adjoint_fused_kernel<REDUCE_TB>+reduce_partials_kernel" if fused_adj else
-                    "lqr_dtau_kernel+adjoint_out_kernel<REDUCE_TB>+reduce_partials_kernel")
+                    ("lqr_dtau_tpe_kernel" if tpe else "lqr_dtau_kernel") + "+adjoint_out_kernel<REDUCE_TB>+reduce_partials_kernel")
         extra_kernels = {red_name: {
             "ms": kt["adjoint_reduced"], "role": "KKT adjoint with the (T,B)-sum of dC,dc,dF,df fused in (shared-parameter "
             "models; not part of the timed step, which materialises the full gradients as the reference does)"}}
