@@ -52,6 +52,13 @@ static bool lqr_tpe_enabled() {
   return v == 1;
 }
 
+// adjoint_out_tpe_kernel has its own switch (DMPC_ADJ_GROUP=1 -> adjoint_out_kernel) on top of DMPC_LQR_GROUP
+static bool lqr_tpe_adj_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DMPC_ADJ_GROUP"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1 && lqr_tpe_enabled();
+}
+
 template <typename R>
 int launch_lqr_rollout_32_8(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
   LqrParams<R> q = p;
@@ -155,6 +162,21 @@ template <typename R>
 int launch_adjoint_out(const AdjOutParams<R>& p, cudaStream_t st, long long* nl) {
   const ShapeInfo si = pick_shape_impl(p.n, p.m);
   const bool red = (p.flags & ADJ_REDUCE_TB) != 0;
+  if (!red && lqr_tpe_adj_enabled()) {                        // s <= 6, materialised gradients: thread per element
+    const int tpb = p.B >= 148 * 64 * 2 ? 64 : 32;
+    const int grid = (p.B + tpb - 1) / tpb;
+#define X(N_, M_)                                                                                            \
+    if (p.n == N_ && p.m == M_) {                                                                            \
+      auto k = adjoint_out_tpe_kernel<R, N_, M_, 64>;                                                        \
+      const size_t sm = (size_t)(tpb / 32) * tpe_adj_warp_reals(N_, M_) * sizeof(R);                         \
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA; \
+      k<<<grid, tpb, sm, st>>>(p);                                                                           \
+      if (nl) ++*nl;                                                                                         \
+      return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;                                    \
+    }
+    X(2, 1) X(3, 1) X(4, 2)
+#undef X
+  }
   const AdjLayout L = adj_layout<R>(p.n, p.m, red && !si.specialised);
   const size_t sb = (size_t)L.stride * sizeof(R);
 #define X(N_, M_, G_) if (si.specialised && p.n == N_ && p.m == M_) \

@@ -65,6 +65,25 @@ __device__ __forceinline__ void tpe_stage(R* dst, int stride, int off, const R* 
     for (int i = lane; i < total; i += 32) { const int le = i / CNT, j = i - le * CNT; tpe_cp(dst + le * stride + off + j, src + i); }
   }
 }
+// the same for element records that are GSTRIDE reals apart in global memory, of which the first CNT are wanted
+template <int CNT, int GSTRIDE, typename R>
+__device__ __forceinline__ void tpe_stage_rows(R* dst, int stride, int off, const R* src, int nv, int lane) {
+  if (nv == 32) {
+    constexpr int Q32 = 32 / CNT, R32 = 32 % CNT;
+    int j = lane % CNT;
+    int d = (lane / CNT) * stride + off + j;
+    int g = (lane / CNT) * GSTRIDE + j;
+#pragma unroll
+    for (int it = 0; it < CNT; ++it) {
+      tpe_cp(dst + d, src + g);
+      j += R32; d += Q32 * stride + R32; g += Q32 * GSTRIDE + R32;
+      if (j >= CNT) { j -= CNT; d += stride - CNT; g += GSTRIDE - CNT; }
+    }
+  } else {
+    const int total = nv * CNT;
+    for (int i = lane; i < total; i += 32) { const int le = i / CNT, j = i - le * CNT; tpe_cp(dst + le * stride + off + j, src + le * GSTRIDE + j); }
+  }
+}
 template <typename R>
 __device__ __forceinline__ void tpe_zero(R* dst, int stride, int off, int cnt, int nv, int lane) {
   const int total = nv * cnt;
@@ -478,6 +497,164 @@ __global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p) {
       __syncwarp();
       slot = slot == DD - 1 ? 0 : slot + 1;
     }
+  }
+}
+
+// shared memory -> global mirror of tpe_stage: the warp writes CNT reals per element for nv consecutive elements as one
+// contiguous, coalesced run
+template <int CNT, typename R>
+__device__ __forceinline__ void tpe_unstage(R* gdst, const R* src, int stride, int off, int nv, int lane) {
+  if (nv == 32) {
+    constexpr int Q32 = 32 / CNT, R32 = 32 % CNT;
+    int j = lane % CNT;
+    int d = (lane / CNT) * stride + off + j;
+#pragma unroll
+    for (int it = 0; it < CNT; ++it) {
+      gdst[lane + 32 * it] = src[d];
+      j += R32; d += Q32 * stride + R32;
+      if (j >= CNT) { j -= CNT; d += stride - CNT; }
+    }
+  } else {
+    const int total = nv * CNT;
+    for (int i = lane; i < total; i += 32) { const int le = i / CNT, j = i - le * CNT; gdst[i] = src[le * stride + off + j]; }
+  }
+}
+
+// lambda / d-lambda recursions + dC, dc, dF, df, dx0 (adjoint_out_kernel without ADJ_REDUCE_TB; reference
+// lqr/differentiable_lqr.py:87-104, 114-134 and mpc/mpc_step.py:383-446) for s <= 6, one thread per element.  Inputs come
+// through the same warp-staged ring as above; the outputs of a step (s*s + s + n*s + n reals per element, 560 bytes at
+// config 2) go back through shared memory too, so that the warp stores them as contiguous runs instead of 32 scattered
+// 8-byte pieces per instruction.
+__host__ __device__ constexpr int tpe_adj_stride_in(int n, int m) { return (2 * n * (n + m) + 3 * n + m + (n + m)) | 1; }
+__host__ __device__ constexpr int tpe_adj_stride_out(int n, int m) { return ((n + m) * (n + m) + (n + m) + n * (n + m) + n) | 1; }
+__host__ __device__ constexpr int tpe_adj_warp_reals(int n, int m) { return 32 * (2 * tpe_adj_stride_in(n, m) + tpe_adj_stride_out(n, m)); }
+
+template <int I, int N, int M, typename R>
+__device__ __forceinline__ void tpe_adj_lam(const R* my, int oC, int oc, int oF, int og, const R (&tau)[N + M], const R (&dt)[N + M],
+                                            const R (&lam)[N], const R (&dlam)[N], bool have_next, bool have_g, R rsgn,
+                                            R (&lamn)[N], R (&dlamn)[N]) {
+  if constexpr (I < N) {
+    constexpr int s = N + M;
+    R a0 = my[oc + I];                                       // lam: c_i + C_i tau, rotated start (as adjoint_out_kernel)
+#pragma unroll
+    for (int c = 0; c < s; ++c) { const int j = (I % s + c) % s; a0 += my[oC + I * s + j] * tau[j]; }
+    R a1 = R(0), b1 = R(0);
+    if (have_next) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) { a1 += my[oF + k * s + I] * lam[k]; b1 += my[oF + k * s + I] * dlam[k]; }
+    }
+    lamn[I] = a0 + a1;
+    const R b0 = tpe_dot_rot<s, I, R>([&](int k) { return my[oC + I * s + k]; }, [&](int k) { return dt[k]; },
+                                      have_g ? rsgn * my[og + I] : R(0));
+    dlamn[I] = b0 + b1;
+    tpe_adj_lam<I + 1, N, M, R>(my, oC, oc, oF, og, tau, dt, lam, dlam, have_next, have_g, rsgn, lamn, dlamn);
+  }
+}
+
+template <typename R, int N, int M, int TPB>
+__global__ void __launch_bounds__(TPB) adjoint_out_tpe_kernel(AdjOutParams<R> p) {
+  constexpr int n = N, m = M, s = N + M;
+  constexpr int SI = tpe_adj_stride_in(N, M), SO = tpe_adj_stride_out(N, M);
+  constexpr int oC = 0, oc = n * s, oF = n * s + n, ox = 2 * n * s + n, ou = ox + n, od = ou + m, og = od + s;   // in slot
+  constexpr int qC = 0, qc = s * s, qF = s * s + s, qf = s * s + s + n * s;                                     // out slot
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = p.T;
+  const int lane = threadIdx.x & 31;
+  const int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  if (e0 >= p.B) return;
+  const int nv = p.B - e0 < 32 ? p.B - e0 : 32;
+  const bool valid = lane < nv;
+  const int ls = valid ? lane : nv - 1;
+  const int e = e0 + ls;
+  const size_t tb = (size_t)p.B;
+  R* wsm = reinterpret_cast<R*>(smem_raw) + (size_t)(threadIdx.x >> 5) * tpe_adj_warp_reals(N, M);
+  R* outs = wsm + 2 * 32 * SI;
+  const bool neg = (p.flags & ADJ_NEGATE) != 0;
+  const R sgn = neg ? R(-1) : R(1);
+  const R rsgn = (p.flags & ADJ_NEG_RHS) ? R(-1) : R(1);
+  const bool quirk_dC = (p.flags & ADJ_QUIRK_DC) != 0, quirk_df = (p.flags & ADJ_QUIRK_DF) != 0;
+  const bool have_g = p.gx != nullptr;
+  const bool write_dc = neg || p.dc != p.dtau;
+
+  // top n rows of C_t and the first n entries of c_t: prefixes of the elements' records (tpe_stage_rows)
+  auto issue_in = [&](int t, int slot) {
+    R* st = wsm + slot * 32 * SI;
+    const size_t i0 = (size_t)t * tb + e0;
+    tpe_stage_rows<n * s, s * s>(st, SI, oC, p.C + i0 * s * s, nv, lane);
+    tpe_stage_rows<n, s>(st, SI, oc, p.c + i0 * s, nv, lane);
+    if (t < T - 1) tpe_stage<n * s>(st, SI, oF, p.F + i0 * n * s, nv, lane);
+    tpe_stage<n>(st, SI, ox, p.x + i0 * n, nv, lane);
+    tpe_stage<m>(st, SI, ou, p.u + i0 * m, nv, lane);
+    tpe_stage<s>(st, SI, od, p.dtau + i0 * s, nv, lane);
+    if (have_g) tpe_stage<n>(st, SI, og, p.gx + i0 * n, nv, lane);
+  };
+  issue_in(T - 1, 0);
+  cp_async_commit();
+  int slot = 0;
+  R lam[n], dlam[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) { lam[i] = R(0); dlam[i] = R(0); }
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t i0 = (size_t)t * tb + e0;
+    if (t > 0) issue_in(t - 1, slot ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    const R* my = wsm + slot * 32 * SI + ls * SI;
+    R* mo = outs + ls * SO;
+    R tau[s], dt[s];
+#pragma unroll
+    for (int j = 0; j < s; ++j) { tau[j] = my[ox + j]; dt[j] = my[od + j]; }      // x | u are adjacent in the slot
+    const bool have_next = t < T - 1;
+    // dF_t = dlam_{t+1} (x) tau_t + lam_{t+1} (x) dtau_t   (t < T-1)
+    if (have_next && valid) {
+#pragma unroll
+      for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < s; ++j) mo[qF + i * s + j] = sgn * (dlam[i] * tau[j] + lam[i] * dt[j]);
+      if (!quirk_df) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) mo[qf + i] = sgn * dlam[i];
+      }
+    }
+    R lamn[n], dlamn[n];
+    tpe_adj_lam<0, N, M, R>(my, oC, oc, oF, og, tau, dt, lam, dlam, have_next, have_g, rsgn, lamn, dlamn);
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < s; ++i)
+#pragma unroll
+        for (int j = 0; j < s; ++j) {
+          const R a = dt[i] * tau[j], b = tau[i] * dt[j];
+          mo[qC + i * s + j] = quirk_dC ? (R(0.5) * a + b) : (sgn * R(0.5) * (a + b));
+        }
+#pragma unroll
+      for (int i = 0; i < s; ++i) mo[qc + i] = sgn * dt[i];
+      if (quirk_df && have_next) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) mo[qf + i] = sgn * dlamn[i];
+      }
+      if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) p.dx0[(size_t)e * n + i] = sgn * dlamn[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) { lam[i] = lamn[i]; dlam[i] = dlamn[i]; }
+    __syncwarp();                                            // the step's outputs are in the out slots
+    tpe_unstage<s * s>(p.dC + i0 * s * s, outs, SO, qC, nv, lane);
+    if (write_dc) tpe_unstage<s>(p.dc + i0 * s, outs, SO, qc, nv, lane);
+    if (have_next) {
+      tpe_unstage<n * s>(p.dF + i0 * n * s, outs, SO, qF, nv, lane);
+      if (p.df) tpe_unstage<n>(p.df + i0 * n, outs, SO, qf, nv, lane);
+    }
+    __syncwarp();                                            // out slots and this input stage may be overwritten
+    slot ^= 1;
+  }
+  // zero-fill the T-th row of dF when F was given with T rows (Q8, mpc_step.py:428)
+  if (p.F_T == T && valid) {
+    R* dFg = p.dF + ((size_t)(T - 1) * tb + e) * n * s;
+#pragma unroll
+    for (int o = 0; o < n * s; ++o) dFg[o] = R(0);
   }
 }
 
