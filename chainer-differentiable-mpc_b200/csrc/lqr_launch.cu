@@ -52,6 +52,22 @@ static bool lqr_tpe_enabled() {
   return v == 1;
 }
 
+// elements per warp of the thread-per-element kernels (lqr_tpe_kernel.cuh).  32 is the measured default.
+// DMPC_LQR_TPE_EPW=auto spreads a small batch over thin warps (8 elements per warp up to B = 148 SMs x 4 schedulers x 8,
+// 16 up to twice that) - the ncu capture says one warp's instruction issue bounds these kernels, so this should pay at
+// config 2; it is parity-checked on the GPU (profiles/tools/epw_check.py: 1.7e-12 against the oracle on four shapes) but the
+// round's GPU budget ended before it could be timed, so it stays opt-in.  DMPC_LQR_TPE_EPW=8|16|32 forces a value.
+static int tpe_elems_per_warp(int B) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("DMPC_LQR_TPE_EPW");
+    forced = !e ? 32 : ((e[0] == 'a') ? -1 : atoi(e));
+    if (forced != -1 && forced != 8 && forced != 16 && forced != 32) forced = 32;
+  }
+  if (forced > 0) return forced;
+  return B <= 148 * 4 * 8 ? 8 : (B <= 148 * 4 * 16 ? 16 : 32);
+}
+
 // adjoint_out_tpe_kernel has its own switch (DMPC_ADJ_GROUP=1 -> adjoint_out_kernel) on top of DMPC_LQR_GROUP
 static bool lqr_tpe_adj_enabled() {
   static int v = -1;
@@ -80,13 +96,14 @@ int launch_lqr_solve(const LqrParams<R>& p, cudaStream_t st, long long* nl) {
   // s <= 6: one thread per element, registers only (lqr_tpe_kernel.cuh); DMPC_LQR_GROUP=1 keeps the group kernel (A/B)
   if (lqr_tpe_enabled()) {
     const int tpb = p.B >= 148 * 64 * 2 ? 64 : 32;            // small batches: more, smaller CTAs so the grid covers the SMs
-    const int grid = (p.B + tpb - 1) / tpb;
+    const int epw = tpe_elems_per_warp(p.B);
+    const int grid = (p.B + epw * (tpb / 32) - 1) / (epw * (tpb / 32));
 #define X(N_, M_)                                                                                            \
     if (p.n == N_ && p.m == M_) {                                                                            \
       auto k = lqr_tpe_kernel<R, N_, M_, 64, 2, 3>;                                                          \
       const size_t sm = (size_t)(tpb / 32) * tpe_lqr_warp_reals(N_, M_, 2, 3) * sizeof(R);                   \
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA; \
-      k<<<grid, tpb, sm, st>>>(p);                                                                           \
+      k<<<grid, tpb, sm, st>>>(p, epw);                                                                        \
       if (nl) ++*nl;                                                                                         \
       return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;                                    \
     }
@@ -113,13 +130,14 @@ int launch_lqr_dtau(const DtauParams<R>& p, cudaStream_t st, long long* nl) {
   const ShapeInfo si = pick_shape_impl(p.n, p.m);
   if (lqr_tpe_enabled()) {                                    // s <= 6: thread per element (lqr_tpe_kernel.cuh)
     const int tpb = p.B >= 148 * 64 * 2 ? 64 : 32;
-    const int grid = (p.B + tpb - 1) / tpb;
+    const int epw = tpe_elems_per_warp(p.B);
+    const int grid = (p.B + epw * (tpb / 32) - 1) / (epw * (tpb / 32));
 #define X(N_, M_)                                                                                            \
     if (p.n == N_ && p.m == M_) {                                                                            \
       auto k = lqr_dtau_tpe_kernel<R, N_, M_, 64, 3>;                                                        \
       const size_t sm = (size_t)(tpb / 32) * tpe_dtau_warp_reals(N_, M_, 3) * sizeof(R);                     \
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA; \
-      k<<<grid, tpb, sm, st>>>(p);                                                                           \
+      k<<<grid, tpb, sm, st>>>(p, epw);                                                                        \
       if (nl) ++*nl;                                                                                         \
       return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;                                    \
     }
@@ -164,13 +182,14 @@ int launch_adjoint_out(const AdjOutParams<R>& p, cudaStream_t st, long long* nl)
   const bool red = (p.flags & ADJ_REDUCE_TB) != 0;
   if (!red && lqr_tpe_adj_enabled()) {                        // s <= 6, materialised gradients: thread per element
     const int tpb = p.B >= 148 * 64 * 2 ? 64 : 32;
-    const int grid = (p.B + tpb - 1) / tpb;
+    const int epw = tpe_elems_per_warp(p.B);
+    const int grid = (p.B + epw * (tpb / 32) - 1) / (epw * (tpb / 32));
 #define X(N_, M_)                                                                                            \
     if (p.n == N_ && p.m == M_) {                                                                            \
       auto k = adjoint_out_tpe_kernel<R, N_, M_, 64>;                                                        \
       const size_t sm = (size_t)(tpb / 32) * tpe_adj_warp_reals(N_, M_) * sizeof(R);                         \
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return DMPC_ERR_CUDA; \
-      k<<<grid, tpb, sm, st>>>(p);                                                                           \
+      k<<<grid, tpb, sm, st>>>(p, epw);                                                                        \
       if (nl) ++*nl;                                                                                         \
       return cudaGetLastError() == cudaSuccess ? DMPC_OK : DMPC_ERR_CUDA;                                    \
     }

@@ -42,6 +42,19 @@ __device__ __forceinline__ void tpe_solve(R (&H)[M][M], R (&X)[M][NC]) {
   }
 }
 
+// Operand staging.  Elements e0 .. e0+31 of one time step are CONTIGUOUS in the reference layout ([T][B][...]), but a
+// thread that loads its own element directly touches a different 128-byte line than its neighbour: every LDG is 32
+// separate L1 requests (measured: the first version of this kernel, direct loads + L2 prefetch, 0.247 ms against the group
+// kernel's 0.259 ms at config 2).  So the WARP copies the step's operands of its elements with coalesced cp.async into a
+// ring of shared-memory stages (one slot per element, odd stride: conflict-free reads), one step ahead in the Riccati
+// sweep and two in the rollout.
+//
+// Elements per warp (epw, a launch argument; 32 by default).  What bounds these kernels at config 2 is ONE warp's
+// instruction issue (ncu, profiles/r2/r2an_c2_tpe.summary.txt: 1670 instructions per Riccati step at one issue every
+// 3.2 cycles, `wait` the top stall, DRAM at 15 %, 1.6 % of the warp slots in use), so a batch that leaves most of the
+// GPU's 592 warp schedulers without a warp can be spread thinner - 16 or 8 elements per warp, the other lanes shadow the
+// last element: idle lanes cost nothing, idle schedulers do, and a warp with fewer elements stages less.  Opt-in
+// (DMPC_LQR_TPE_EPW, lqr_launch.cu): parity-checked on the GPU, not yet timed.
 template <typename R>
 __device__ __forceinline__ void tpe_cp(R* sdst, const R* g) {
   if (sizeof(R) == 8) cp_async8(sdst, g); else cp_async4(sdst, g);
@@ -101,7 +114,7 @@ __host__ __device__ constexpr int tpe_lqr_warp_reals(int n, int m, int ds, int d
 }
 
 template <typename R, int N, int M, int TPB, int DS, int DR>
-__global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
+__global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p, int epw) {
   constexpr int n = N, m = M, s = N + M, NC = N + 1 + M;
   constexpr int SF = tpe_lqr_stride_f(N, M), SR = tpe_lqr_stride_r(N, M);
   constexpr int oC = 0, oc = s * s, oF = s * s + s, of = s * s + s + n * s;      // sweep slot: C | c | F | f
@@ -110,9 +123,9 @@ __global__ void __launch_bounds__(TPB) lqr_tpe_kernel(LqrParams<R> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = p.T;
   const int lane = threadIdx.x & 31;
-  const int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31);                   // first element of this warp
+  const int e0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * epw;      // first element of this warp
   if (e0 >= p.B) return;                                                          // whole warp (only __syncwarp below)
-  const int nv = p.B - e0 < 32 ? p.B - e0 : 32;                                   // elements of this warp
+  const int nv = p.B - e0 < epw ? p.B - e0 : epw;                                   // elements of this warp
   const bool valid = lane < nv;
   const int ls = valid ? lane : nv - 1;                                           // padding lanes shadow the last element
   const int e = e0 + ls;
@@ -392,7 +405,7 @@ __device__ __forceinline__ void tpe_dtau_dx(const R* Ft, const R (&dx)[N + M], R
 }
 
 template <typename R, int N, int M, int TPB, int DD>
-__global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p) {
+__global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p, int epw) {
   constexpr int n = N, m = M, s = N + M, fsz = M * M + N * M;
   constexpr int SD = tpe_dtau_stride(N, M);
   constexpr int oF = 0, oA = n * s, ogx = n * s + fsz, ogu = n * s + fsz + n;      // sweep 1 slot: F | Quu^-1 | Qxu | gx | gu
@@ -400,9 +413,9 @@ __global__ void __launch_bounds__(TPB) lqr_dtau_tpe_kernel(DtauParams<R> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = p.T;
   const int lane = threadIdx.x & 31;
-  const int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  const int e0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * epw;
   if (e0 >= p.B) return;
-  const int nv = p.B - e0 < 32 ? p.B - e0 : 32;
+  const int nv = p.B - e0 < epw ? p.B - e0 : epw;
   const bool valid = lane < nv;
   const int ls = valid ? lane : nv - 1;
   const int e = e0 + ls;
@@ -552,7 +565,7 @@ __device__ __forceinline__ void tpe_adj_lam(const R* my, int oC, int oc, int oF,
 }
 
 template <typename R, int N, int M, int TPB>
-__global__ void __launch_bounds__(TPB) adjoint_out_tpe_kernel(AdjOutParams<R> p) {
+__global__ void __launch_bounds__(TPB) adjoint_out_tpe_kernel(AdjOutParams<R> p, int epw) {
   constexpr int n = N, m = M, s = N + M;
   constexpr int SI = tpe_adj_stride_in(N, M), SO = tpe_adj_stride_out(N, M);
   constexpr int oC = 0, oc = n * s, oF = n * s + n, ox = 2 * n * s + n, ou = ox + n, od = ou + m, og = od + s;   // in slot
@@ -560,9 +573,9 @@ __global__ void __launch_bounds__(TPB) adjoint_out_tpe_kernel(AdjOutParams<R> p)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = p.T;
   const int lane = threadIdx.x & 31;
-  const int e0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  const int e0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * epw;
   if (e0 >= p.B) return;
-  const int nv = p.B - e0 < 32 ? p.B - e0 : 32;
+  const int nv = p.B - e0 < epw ? p.B - e0 : epw;
   const bool valid = lane < nv;
   const int ls = valid ? lane : nv - 1;
   const int e = e0 + ls;
