@@ -6,8 +6,8 @@
 // Why: lqr_solve_kernel gives such an element a group of 4-8 lanes that exchange every intermediate through shared
 // memory, with seven group barriers and a generic LU per time step; at s = 6 a Riccati step is ~700 flops, and the group
 // kernel spends ~7900 cycles on it (profiles/r2/r2y_bench_c2.json: 0.201 ms for T = 50) - dependent-chain latency, not
-// bandwidth (7 % of HBM).  A thread that owns the element needs no barrier, no shared memory, and its m <= 2 elimination
-// is a handful of FMAs.  Same contract as lqr_solve_kernel (LqrParams, every flag); pivoting as there (first maximum
+// bandwidth (7 % of HBM).  A thread that owns the element needs no barrier and its m <= 2 elimination is a handful of
+// FMAs; shared memory only stages the operands (below).  Same contract as lqr_solve_kernel (LqrParams, every flag); pivoting as there (first maximum
 // wins), the pivots enter through their reciprocals.
 #pragma once
 #include "lqr_kernels.cuh"
@@ -24,8 +24,8 @@ __device__ __forceinline__ void tpe_solve(R (&H)[M][M], R (&X)[M][NC]) {
 #pragma unroll
       for (int j = 0; j < NC; ++j) { const R t = X[0][j]; X[0][j] = X[1][j]; X[1][j] = t; }
     }
-    // two reciprocals per step instead of a division per column and row: the divisions (and the branch around each
-    // one's slow path) were a third of the step's dependent chain
+    // two reciprocals per step instead of a guarded division per column and row (fourteen at n = 4, m = 2, each with a
+    // branch around its slow path that keeps the compiler from interleaving them)
     const R r0 = R(1) / H[0][0];
     const R l = H[1][0] * r0;
     const R r1 = R(1) / (H[1][1] - l * H[0][1]);
