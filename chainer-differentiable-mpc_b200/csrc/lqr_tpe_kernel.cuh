@@ -49,12 +49,13 @@ __device__ __forceinline__ void tpe_solve(R (&H)[M][M], R (&X)[M][NC]) {
 // ring of shared-memory stages (one slot per element, odd stride: conflict-free reads), one step ahead in the Riccati
 // sweep and two in the rollout.
 //
-// Elements per warp (epw, a launch argument; 32 by default).  What bounds these kernels at config 2 is ONE warp's
-// instruction issue (ncu, profiles/r2/r2an_c2_tpe.summary.txt: 1670 instructions per Riccati step at one issue every
-// 3.2 cycles, `wait` the top stall, DRAM at 15 %, 1.6 % of the warp slots in use), so a batch that leaves most of the
-// GPU's 592 warp schedulers without a warp can be spread thinner - 16 or 8 elements per warp, the other lanes shadow the
-// last element: idle lanes cost nothing, idle schedulers do, and a warp with fewer elements stages less.  Opt-in
-// (DMPC_LQR_TPE_EPW, lqr_launch.cu): parity-checked on the GPU, not yet timed.
+// Elements per warp (epw, a launch argument; 32 by default).  At config 2 the kernel's duration is ONE warp's serial
+// instruction stream (ncu, profiles/r2/r2an_c2_tpe.summary.txt: 1670 instructions per Riccati step at one issue every
+// 3.2 cycles, `wait` the top stall, DRAM at 15 %, 1.6 % of the warp slots in use), and ~30 % of that stream is this
+// staging.  A batch that leaves most of the GPU's 592 warp schedulers idle anyway can be spread thinner - 16 or 8 elements
+// per warp, the other lanes shadow the last element - so that each warp stages half or a quarter as much; the recursion's
+// own instructions do not shrink, so the gain is bounded by ~1.3x.  Opt-in (DMPC_LQR_TPE_EPW, lqr_launch.cu):
+// parity-checked on the GPU, not yet timed.
 template <typename R>
 __device__ __forceinline__ void tpe_cp(R* sdst, const R* g) {
   if (sizeof(R) == 8) cp_async8(sdst, g); else cp_async4(sdst, g);
